@@ -1,0 +1,175 @@
+"""numpy model of the DEVICE algorithm (test infrastructure, not the product).
+
+The CUDA driver (fortran_davidson_b200/csrc/solver.cu) does not run the reference's statements
+literally: it keeps V / AV / BV resident and incremental, takes residuals from the stored
+products, orthonormalises only the new block (project out V twice + SVQB), and solves the
+projected problems with a parallel-ordering two-sided Jacobi.  This file restates exactly that
+flow in numpy so that the CPU suite can check, without a GPU, that the flow is
+subspace-equivalent to the reference (same iteration count, same eigenvalues) -- see
+tests/test_device_model.py.  The kernels' arithmetic is mirrored step by step; names follow
+solver.cu.
+"""
+import numpy as np
+
+EPS = 2.0 ** -52
+
+
+def round_robin_pairs(kp, r):
+    """Pairs of round r (0..kp-2) of the chess-tournament ordering on kp (even) players."""
+    m = kp - 1
+    pairs = [(kp - 1, r % m)]
+    for i in range(1, kp // 2):
+        a = (r + i) % m
+        b = (r - i + m) % m
+        pairs.append((a, b))
+    return [(min(p, q), max(p, q)) for (p, q) in pairs]
+
+
+def jacobi_eigh(S_in, max_sweeps=40):
+    """Two-sided Jacobi with the round-robin parallel ordering; reads the upper triangle only
+    (DSYEV 'U' semantics, lapack_wrapper.f90:62,76).  Returns ascending eigenvalues + vectors."""
+    k = S_in.shape[0]
+    S = np.triu(S_in) + np.triu(S_in, 1).T
+    kp = k + (k & 1)
+    if kp != k:
+        S = np.pad(S, ((0, 1), (0, 1)))
+    V = np.eye(kp)
+    normF = np.sqrt((S * S).sum())
+    abs_thr = EPS * normF / (16.0 * kp)
+    for sweep in range(max_sweeps):
+        rotated = False
+        for r in range(kp - 1):
+            pairs = round_robin_pairs(kp, r)
+            J = np.eye(kp)
+            for (p, q) in pairs:
+                if p >= k or q >= k:
+                    continue
+                apq = S[p, q]
+                app, aqq = S[p, p], S[q, q]
+                if abs(apq) <= abs_thr or abs(apq) <= EPS * np.sqrt(abs(app) * abs(aqq)):
+                    continue
+                rotated = True
+                tau = (aqq - app) / (2.0 * apq)
+                t = (1.0 if tau >= 0 else -1.0) / (abs(tau) + np.sqrt(1.0 + tau * tau))
+                c = 1.0 / np.sqrt(1.0 + t * t)
+                s = t * c
+                J[p, p] = c; J[q, q] = c; J[p, q] = s; J[q, p] = -s
+            S = J.T @ S @ J
+            S = 0.5 * (S + S.T)
+            V = V @ J
+        if not rotated:
+            break
+    w = np.diag(S)[:k].copy()
+    order = np.argsort(w, kind="stable")
+    return w[order], V[:k, :k][:, order]
+
+
+def sygv(Ap, Bp):
+    """Generalized RR: Bp = U S U^T, T = U S^-1/2, C = T^T Ap T, C Z = Z theta, Y = T Z
+    (DSYGV itype=1 semantics: Y^T Bp Y = I, ascending theta; lapack_wrapper.f90:59,73)."""
+    s, U = jacobi_eigh(Bp)
+    if s.min() <= 0:
+        raise RuntimeError("second_matrix projection not positive definite")
+    T = U / np.sqrt(s)
+    Apu = np.triu(Ap) + np.triu(Ap, 1).T
+    C = T.T @ Apu @ T
+    theta, Z = jacobi_eigh(C)
+    return theta, T @ Z
+
+
+def svqb(C, V, passes=2):
+    """Orthonormalise the block C against V (orthonormal) and itself."""
+    n, b = C.shape
+    cn = np.sqrt((C * C).sum(axis=0))
+    C = C / np.where(cn > 0, cn, 1.0)
+    for _ in range(passes):
+        C = C - V @ (V.T @ C)
+        G = C.T @ C
+        d = np.diag(G).copy()
+        D = np.where(d > 0, 1.0 / np.sqrt(np.where(d > 0, d, 1.0)), 0.0)
+        Gs = G * D[:, None] * D[None, :]
+        s, U = jacobi_eigh(Gs)
+        smax = s.max()
+        thr = smax * b * EPS * 16
+        bad = s <= thr
+        T = (U * D[:, None]) / np.sqrt(np.where(bad, 1.0, s))
+        C = C @ T
+        if bad.any():
+            rng = np.random.default_rng(1234)
+            C[:, bad] = rng.uniform(-1, 1, size=(n, int(bad.sum())))
+    return C
+
+
+def solve_dense(A, lowest, method, max_iterations, tolerance, max_dim_sub=None, B=None, free_semantics=False,
+                diagA=None, diagB=None, apply_A=None, apply_B=None):
+    n = A.shape[0] if A is not None else diagA.size
+    gev = (B is not None) or (apply_B is not None)
+    mulA = (lambda X: A @ X) if apply_A is None else apply_A
+    mulB = (lambda X: B @ X) if apply_B is None else apply_B
+    dA = np.diag(A).copy() if diagA is None else diagA
+    dB = (np.diag(B).copy() if B is not None else np.ones(n)) if diagB is None else diagB
+    k = 2 * lowest
+    max_dim = max_dim_sub if max_dim_sub else 10 * lowest
+    idx = np.argsort(dA, kind="stable")[:k]
+    V = np.zeros((n, k)); V[idx, np.arange(k)] = 1.0
+    AV = mulA(V)
+    BV = mulB(V) if gev else None
+    Ap = V.T @ AV
+    Bp = V.T @ BV if gev else None
+    has_conv = np.zeros(lowest, dtype=bool)
+    trace_k, trace_err = [], []
+    iters = max_iterations + 1
+    theta = Y = None
+    for it in range(1, max_iterations + 1):
+        if gev:
+            theta, Y = sygv(Ap, Bp)
+        else:
+            theta, Y = jacobi_eigh(Ap)
+        R = AV @ Y - ((BV if gev else V) @ Y) * theta[None, :]
+        errs = np.sqrt((R[:, :lowest] ** 2).sum(axis=0))
+        trace_k.append(k); trace_err.append(errs.max())
+        if free_semantics:
+            done = bool((errs < tolerance).all())
+        else:
+            has_conv |= errs < tolerance
+            done = bool(has_conv.all())
+        if done:
+            iters = it
+            break
+        if k <= max_dim:
+            if 2 * k > n:
+                raise RuntimeError("basis larger than the matrix")
+            if method == "DPR":
+                C = R / (theta[None, :] * dB[:, None] - dA[:, None])
+            else:
+                raise NotImplementedError
+            Q = svqb(C, V)
+            AQ = mulA(Q)
+            Vn = np.hstack([V, Q])
+            Apn = np.zeros((2 * k, 2 * k)); Apn[:k, :k] = Ap
+            blk = Vn.T @ AQ
+            Apn[:, k:] = blk; Apn[k:, :k] = blk[:k, :].T
+            AV = np.hstack([AV, AQ]); Ap = Apn
+            if gev:
+                BQ = mulB(Q)
+                Bpn = np.zeros((2 * k, 2 * k)); Bpn[:k, :k] = Bp
+                blk = Vn.T @ BQ
+                Bpn[:, k:] = blk; Bpn[k:, :k] = blk[:k, :].T
+                BV = np.hstack([BV, BQ]); Bp = Bpn
+            V = Vn
+            k *= 2
+        else:
+            Yc = Y[:, :2 * lowest]
+            V = V @ Yc; AV = AV @ Yc
+            if gev:
+                BV = BV @ Yc
+                # collapsed basis is B-orthonormal; make it 2-orthonormal again (same span)
+                G = V.T @ V
+                s, U = jacobi_eigh(G)
+                T = U / np.sqrt(s)
+                V = V @ T; AV = AV @ T; BV = BV @ T
+                Bp = V.T @ BV
+            Ap = V.T @ AV
+            k = 2 * lowest
+    X = V @ Y[:, :lowest]
+    return theta[:lowest].copy(), X, iters, np.array(trace_k), np.array(trace_err)
