@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- time-to-converge of the block Davidson solver on BASELINE.json's headline workload.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" is one complete solve (generalized_eigensolver, DPR) of the dense fp64 diagonal-dominant
+matrix of BASELINE.json configs[2]: n = 100,000 (80 GB), lowest = 16, max_dim_sub = 160 (default
+10*lowest), tol 1e-8, generate_diagonal_dominant(n, 1e-4) from the counter-based stream, seed 0.
+`value` times the solve with the matrix already resident in HBM (row-block sharded over the N ranks:
+strong scaling); `e2e` times the same solve through the drop-in C-ABI call with the matrix in (pinned)
+HOST memory, upload included.  The reference arm runs the CPU restatement of the reference
+(oracle/, linked to real LAPACK) on the host cores on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "time_to_converge_dense_fp64_n100k_lowest16_DPR"
+UNIT = "s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=100000)
+    ap.add_argument("--lowest", type=int, default=16)
+    ap.add_argument("--max-dim", type=int, default=0, help="0 = reference default 10*lowest")
+    ap.add_argument("--sparsity", type=float, default=1e-4)
+    ap.add_argument("--tol", type=float, default=1e-8)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--matvec-impl", type=int, default=0)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop = threading.Event()
+        self.t = None
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split("\n")[0].split(",")]
+                if len(f) >= 9:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for nm, v in zip(names, s[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][2]),
+                "power_w_max": max(float(s[3]) for s in self.samples), "samples": len(self.samples),
+                "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (driver-measured copy)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md), MEASURED_PEAKS.json absent"
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(args, steps, warmup, budget_s):
+    """Times the oracle (CPU restatement of the reference + real LAPACK) on the host cores on a bounded
+    sample: same generator / lowest / max_dim / tolerance at a smaller n, extrapolated ~ n^2."""
+    from oracle import oracle as orc
+    cores = os.cpu_count() or 1
+    orc.set_num_threads(cores)
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    per_solve = budget_s / max(1, steps + warmup)
+    # ~20 s at n = 20,000 on 16 cores (k DGEMVs per iteration stream A k times), cost ~ n^2
+    n_s = int(min(args.n, max(4000, 20000 * (per_solve / 20.0) ** 0.5)) // 1000 * 1000)
+    n_s = max(min(n_s, 20000, args.n), min(args.n, 2000))
+    A = orc.generate_diagonal_dominant(n_s, args.sparsity, None, 0)
+    md = args.max_dim or None
+    times = []
+    r = None
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        r = orc.generalized_eigensolver(A, args.lowest, "DPR", 1000, args.tol, md)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    t_sample = sum(times) / len(times)
+    scale = (args.n / n_s) ** 2
+    return {"value": t_sample * scale, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": ("oracle/ (C++ restatement of davidson.f90 + scipy OpenBLAS LAPACK; no Fortran compiler in the "
+                       "image, so the reference itself cannot be built): full solve at n=%d, lowest=%d, DPR, %d "
+                       "iterations, %.3f s measured (mean of %d), extrapolated x(n/n_sample)^2 = x%.1f to n=%d"
+                       % (n_s, args.lowest, r.iters, t_sample, len(times), scale, args.n)),
+            "sample_n": n_s, "sample_seconds": t_sample, "sample_iters": int(r.iters), "extrapolation_factor": scale}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_reference_run(args, args.steps, args.warmup, budget_s=150.0)
+    line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": cb["value"] * 1e3, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": workload_config(args, 1), "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(args, n_gpus):
+    md = args.max_dim or 10 * args.lowest
+    return {"workload": "BASELINE.json configs[2]: dense fp64 generate_diagonal_dominant(n=%d, sparsity=%g, seed 0), "
+                        "lowest=%d, DPR, max_dim_sub=%d, tol=%g, row-block sharded over %d GPU(s)"
+                        % (args.n, args.sparsity, args.lowest, md, args.tol, n_gpus),
+            "n": args.n, "lowest": args.lowest, "method": "DPR", "max_dim_sub": md, "tolerance": args.tol,
+            "l2_policy": "matrix (%.1f GB) is far larger than L2 (126 MB): no flush needed" % (8e-9 * args.n * args.n),
+            "parallelism": "row-block x%d" % n_gpus}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import fortran_davidson_b200 as fd
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d does not match WORLD_SIZE %d" % (args.gpus, world))
+    torch.cuda.set_device(local_rank)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        ids = [fd.DavidsonSolver.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        solver = fd.DavidsonSolver(local_rank, rank, world, ids[0])
+    else:
+        solver = fd.DavidsonSolver(local_rank)
+    solver.set_matvec_impl(args.matvec_impl)
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if not distributed:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n, L = args.n, args.lowest
+    md = args.max_dim or None
+    t0 = time.perf_counter()
+    solver.generate_diagonal_dominant(0, n, args.sparsity, None, 0)
+    barrier()
+    gen_s = time.perf_counter() - t0
+
+    # ---- warm-up
+    for _ in range(args.warmup):
+        ev, _vec, iters = solver.solve(L, "DPR", 1000, args.tol, md, want_vectors=True)
+
+    # ---- timed region: exactly K solves, barrier + synchronize on both sides, device time = CUDA events on the
+    # solver's own stream (dav_stats_t.solve_ms), max over ranks
+    dev_ms, mv_ms, mv_launch, launches = [], [], [], []
+    per_launch = []
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            ev, vec, iters = solver.solve(L, "DPR", 1000, args.tol, md, want_vectors=True)
+            st = solver.stats()
+            dev_ms.append(st.solve_ms)
+            mv_ms.append(st.matvec_ms)
+            mv_launch.append(st.matvec_launches)
+            launches.append(st.kernel_launches)
+        barrier()
+        wall_ms = (time.perf_counter() - w0) * 1e3 / args.steps
+    st = solver.stats()
+    ms_per_step = max_over_ranks(sum(dev_ms) / len(dev_ms))
+    wall_ms = max_over_ranks(wall_ms)
+    value = ms_per_step * 1e-3
+
+    # ---- residual check of the result (property at full size): ||A v - lambda v|| <= tol
+    av = solver.block_matvec(0, vec)
+    r0, r1 = solver.rows()
+    res2 = ((av - vec[r0:r1] * ev) ** 2).sum(axis=0)
+    if distributed:
+        t = torch.tensor(res2, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        res2 = t.cpu().numpy()
+    max_res = float(np.sqrt(res2).max())
+
+    # ---- roofline of the dominant kernel (the block matvec): per-width timings with events on the solver stream
+    hbm_peak, hbm_src = measured_peaks()
+    nl = r1 - r0
+    widths = sorted(set([16] + [int(k) for k in st.trace_k[:max(st.trace_len - 1, 1)]]))
+    per_width = {}
+    for b in widths:
+        ms = solver.bench_block_matvec(0, b, 5)
+        ms_b = max_over_ranks(float(np.median(ms)))
+        byts = 8.0 * nl * n + 8.0 * n * b + 8.0 * nl * b
+        per_width[str(b)] = {"ms": ms_b, "GBps": byts / ms_b * 1e-6, "TFLOPs": 2.0 * nl * n * b / ms_b * 1e-9,
+                             "hbm_frac": byts / ms_b * 1e-6 / hbm_peak}
+    # FP64 peak: not in MEASURED_PEAKS.json -> measured live (cuBLAS DGEMM through torch; denominator only)
+    a = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+    bb = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+    torch.matmul(a, bb)
+    best = 1e9
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, bb); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    p64 = 2.0 * 8192 ** 3 / best * 1e-9
+    del a, bb
+    torch.cuda.empty_cache()
+    dom_b = int(st.last_matvec_b)
+    dom = per_width.get(str(dom_b), per_width[str(widths[-1])])
+    in_solve_ms = max_over_ranks(sum(mv_ms) / len(mv_ms))
+    roofline = {"bound": "tensor", "achieved": dom["TFLOPs"], "peak": p64, "unit": "TFLOP/s",
+                "frac": dom["TFLOPs"] / p64, "traffic": None,
+                "kernel": "matvec_kernel (TMA + mbarrier + FP64 DMMA, stream-K), widest block of the solve b=%d: "
+                          "2*nl*n*b flops / launch; FP64-bound above b~23 (b/4 flop per byte vs %.1f flop/B machine "
+                          "balance)" % (dom_b, p64 * 1e3 / hbm_peak),
+                "peak_source": "measured live: torch.matmul fp64 8192^3 (cuBLAS DGEMM), best of 3",
+                "hbm_view": {"b": 16, "achieved": per_width["16"]["GBps"], "peak": hbm_peak, "unit": "GB/s",
+                             "frac": per_width["16"]["hbm_frac"], "peak_source": hbm_src,
+                             "note": "narrow block (HBM-bound regime): algorithmic bytes 8*nl*n + 8*n*b + 8*nl*b"},
+                "per_width": per_width, "matvec_ms_in_solve": in_solve_ms,
+                "matvec_share_of_step": in_solve_ms / ms_per_step}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, args.gpus),
+            "iterations": int(iters) if iters is not None else None,
+            "basis_schedule": [int(k) for k in st.trace_k[:st.trace_len]],
+            "eigenvalues_head": [float(x) for x in ev[:4]], "max_residual": max_res,
+            "wall_ms_per_step": wall_ms, "generate_s": gen_s,
+            "phase_ms": {"matvec": st.matvec_ms, "rayleigh_ritz": st.rr_ms, "orthonormalise": st.orth_ms,
+                         "residual_dpr": st.resid_ms, "projection": st.proj_ms, "init": st.init_ms},
+            "gpu_launches": int(sum(launches) / len(launches)), "matvec_launches": int(mv_launch[-1]),
+            "clocks": clocks.summary(), "roofline": roofline}
+
+    # ---- end to end through the drop-in C ABI with HOST buffers (upload inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        try:
+            e2e = run_e2e(args, solver, fd, torch, dist, distributed, rank, world, n, L, md, barrier, max_over_ranks)
+        except Exception as ex:  # report, never fake
+            e2e = {"value": None, "unit": UNIT, "error": repr(ex)[:300]}
+    line["e2e"] = e2e if e2e is not None else {"value": None, "unit": UNIT, "skipped": "--no-e2e"}
+
+    # ---- CPU baseline on the box's host cores (rank 0, N=1 only)
+    if rank == 0 and args.gpus == 1 and not args.no_cpu:
+        try:
+            line["cpu_baseline"] = cpu_reference_run(args, 1, 0, budget_s=25.0)
+        except Exception as ex:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "error": repr(ex)[:300]}
+    solver.close()
+    if rank == 0:
+        print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, solver, fd, torch, dist, distributed, rank, world, n, L, md, barrier, max_over_ranks):
+    """Each step: host matrix (pinned) -> device upload -> solve -> eigenpairs back on the host."""
+    import numpy as np
+    r0, r1 = solver.rows()
+    nl = r1 - r0
+    need_gb = 8e-9 * nl * n
+    avail_gb = 0.0
+    for ln in open("/proc/meminfo"):
+        if ln.startswith("MemAvailable"):
+            avail_gb = float(ln.split()[1]) * 1e-6
+    note = None
+    if need_gb * world > 0.8 * avail_gb:
+        return {"value": None, "unit": UNIT,
+                "skipped": "host RAM: need %.0f GB for the host copy, %.0f GB available" % (need_gb * world, avail_gb)}
+    # host copy of this rank's row block: column-major nl x n (== C-order (n, nl)), page-locked in place
+    # (torch's pinned allocator would round 80 GB up to 128 GB)
+    host = np.empty((n, nl), dtype=np.float64)
+    ptr = host.ctypes.data
+    rt = torch.cuda.cudart()
+    err = rt.cudaHostRegister(ptr, host.nbytes, 0)
+    pinned = (int(err) == 0)
+    # fill it from the device-generated matrix (once, untimed)
+    fd._lib.check(fd.lib().dav_matrix_download(solver._h, C.c_int(0), C.c_void_p(ptr), C.c_int64(max(nl, 1))))
+    solver.clear(0)  # the e2e path allocates its own device copy
+    torch.cuda.empty_cache()
+    times = []
+    ev = None
+    steps = max(1, args.e2e_steps)
+    for i in range(1 + steps):  # one untimed warm-up
+        barrier()
+        t0 = time.perf_counter()
+        if world == 1:
+            ev_ = np.zeros(L); vec_ = np.zeros((n, L), order="F"); it_ = C.c_int(0)
+            fd._lib.check(fd.lib().dav_generalized_eigensolver_dense(
+                C.c_int64(n), C.c_void_p(ptr), C.c_int64(n), None, C.c_int64(n), C.c_int(L), b"DPR", C.c_int(1000),
+                C.c_double(args.tol), C.c_int(md or 0), ev_.ctypes.data_as(C.POINTER(C.c_double)),
+                vec_.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(n), C.byref(it_)))
+            ev = ev_
+        else:
+            # sharded: every rank uploads its own row block (host pointer offset so that row r0 is its first row)
+            solver.upload_ptr(0, n, ptr - 8 * r0, nl)
+            ev, _v, _it = solver.solve(L, "DPR", 1000, args.tol, md, want_vectors=True)
+            solver.clear(0)
+        barrier()
+        if i > 0:
+            times.append(time.perf_counter() - t0)
+    t = max_over_ranks(sum(times) / len(times))
+    if pinned:
+        rt.cudaHostUnregister(ptr)
+    return {"value": t, "unit": UNIT, "h2d_bytes_per_step": int(8 * nl * n * world),
+            "d2h_bytes_per_step": int(8 * n * L + 8 * L), "steps": steps,
+            "api": "dav_generalized_eigensolver_dense (host pointers, pinned)" if world == 1 else
+                   "dav_matrix_upload + dav_solve per rank (host row blocks, pinned)",
+            "eigenvalue0": float(ev[0]), "host_memory": "page-locked" if pinned else "pageable", "note": note}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,162 @@
+// Generic SIMT FP64 GEMM for the tall-skinny shapes around the block matvec:
+//   NN  C(M x N) = alpha * A(M x K) * B(K x N) + beta * C      M = local rows (huge), K,N <= few hundred
+//   TN  C(M x N) = alpha * A(K x M)^T * B(K x N) + beta * C    K = local rows (huge) -> split-K
+// Replaces the reference's lapack_matmul / DGEMM call sites other than the A*V stream
+// (davidson.f90:131,159,218,223,380-381,397,407-410,438; lapack_wrapper.f90:279-328).
+// 64x64x16 tiles, 256 threads, 4x4 register microtile; split-K partials are summed in a fixed
+// order by a second kernel, so results are bit-reproducible run to run.
+#include "kernels.cuh"
+
+namespace dav {
+
+thread_local long long g_kernel_launches = 0;
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, LDS_ = 66, NT = 256;
+
+template <bool TA>
+__global__ void __launch_bounds__(NT) gemm_kernel(int64_t M, int64_t N, int64_t K, int64_t Kchunk, double alpha,
+                                                  const double* __restrict__ A, int64_t lda,
+                                                  const double* __restrict__ B, int64_t ldb, double beta,
+                                                  double* __restrict__ C, int64_t ldc, double* __restrict__ ws,
+                                                  int splits) {
+  __shared__ __align__(16) double As[BK][LDS_];
+  __shared__ __align__(16) double Bs[BK][LDS_];
+  const int tid = threadIdx.x;
+  const int tm = tid % 16, tn = tid / 16;
+  const int64_t m0 = (int64_t)blockIdx.x * BM, n0 = (int64_t)blockIdx.y * BN;
+  const int z = blockIdx.z;
+  const int64_t kbeg = (int64_t)z * Kchunk;
+  const int64_t kend = min(K, kbeg + Kchunk);
+
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+
+  for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
+    // ---- load A tile into As[k][m]
+    if (!TA) {
+      const int m = tid % 64, kq = tid / 64;
+      const int64_t gm = m0 + m;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int k = kq + 4 * r;
+        const int64_t gk = k0 + k;
+        As[k][m] = (gm < M && gk < kend) ? A[gm + gk * lda] : 0.0;
+      }
+    } else {
+      const int k = tid % 16, mq = tid / 16;
+      const int64_t gk = k0 + k;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int m = mq + 16 * r;
+        const int64_t gm = m0 + m;
+        As[k][m] = (gm < M && gk < kend) ? A[gk + gm * lda] : 0.0;
+      }
+    }
+    // ---- load B tile into Bs[k][j]
+    {
+      const int k = tid % 16, jq = tid / 16;
+      const int64_t gk = k0 + k;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int j = jq + 16 * r;
+        const int64_t gj = n0 + j;
+        Bs[k][j] = (gj < N && gk < kend) ? B[gk + gj * ldb] : 0.0;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const double2 a01 = *reinterpret_cast<const double2*>(&As[kk][tm * 4]);
+      const double2 a23 = *reinterpret_cast<const double2*>(&As[kk][tm * 4 + 2]);
+      const double2 b01 = *reinterpret_cast<const double2*>(&Bs[kk][tn * 4]);
+      const double2 b23 = *reinterpret_cast<const double2*>(&Bs[kk][tn * 4 + 2]);
+      const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+      const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  if (splits == 1) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t gj = n0 + tn * 4 + j;
+      if (gj >= N) continue;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t gm = m0 + tm * 4 + i;
+        if (gm >= M) continue;
+        double* c = C + gm + gj * ldc;
+        *c = (beta == 0.0) ? alpha * acc[i][j] : alpha * acc[i][j] + beta * (*c);
+      }
+    }
+  } else {
+    double* w = ws + (size_t)z * (size_t)M * (size_t)N;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t gj = n0 + tn * 4 + j;
+      if (gj >= N) continue;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t gm = m0 + tm * 4 + i;
+        if (gm >= M) continue;
+        w[gm + gj * M] = acc[i][j];
+      }
+    }
+  }
+}
+
+__global__ void splitk_reduce_kernel(int64_t M, int64_t N, int splits, double alpha, const double* __restrict__ ws,
+                                     double beta, double* __restrict__ C, int64_t ldc) {
+  const int64_t total = M * N;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int z = 0; z < splits; ++z) s += ws[(size_t)z * total + e];
+    const int64_t m = e % M, j = e / M;
+    double* c = C + m + j * ldc;
+    *c = (beta == 0.0) ? alpha * s : alpha * s + beta * (*c);
+  }
+}
+
+}  // namespace
+
+void gemm(cudaStream_t s, bool transA, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+          const double* B, int64_t ldb, double beta, double* C, int64_t ldc, double* ws, size_t ws_doubles) {
+  if (M <= 0 || N <= 0) return;
+  const int64_t gx = ceil_div(M, BM), gy = ceil_div(N, BN);
+  int splits = 1;
+  if (K > 4096 && gx * gy < 592) {  // long reduction, few output tiles: split K over the grid
+    splits = (int)std::min<int64_t>(ceil_div(592, gx * gy), ceil_div(K, 1024));
+    const size_t need = (size_t)M * (size_t)N;
+    if (ws == nullptr || need == 0) splits = 1;
+    else splits = (int)std::min<size_t>((size_t)splits, ws_doubles / need);
+    if (splits < 1) splits = 1;
+  }
+  const int64_t Kchunk = round_up(ceil_div(std::max<int64_t>(K, 1), splits), BK);
+  splits = (int)ceil_div(std::max<int64_t>(K, 1), Kchunk);
+  if (gy > 65535 || splits > 65535) DAV_THROW(DAV_ERR_INVALID, "gemm grid too large");
+  dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)splits);
+  if (transA)
+    gemm_kernel<true><<<grid, NT, 0, s>>>(M, N, K, Kchunk, alpha, A, lda, B, ldb, beta, C, ldc, ws, splits);
+  else
+    gemm_kernel<false><<<grid, NT, 0, s>>>(M, N, K, Kchunk, alpha, A, lda, B, ldb, beta, C, ldc, ws, splits);
+  CK_LAUNCH();
+  ++g_kernel_launches;
+  if (splits > 1) {
+    const int64_t total = M * N;
+    const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 1184);
+    splitk_reduce_kernel<<<blocks, 256, 0, s>>>(M, N, splits, alpha, ws, beta, C, ldc);
+    CK_LAUNCH();
+    ++g_kernel_launches;
+  }
+}
+
+}  // namespace dav

@@ -1,0 +1,98 @@
+// Launchers of every device kernel of the library (definitions in the .cu files next to this one).
+#pragma once
+#include "common.cuh"
+
+namespace dav {
+
+// Every launcher bumps this counter (bench.py reports it as `gpu_launches`).
+extern thread_local long long g_kernel_launches;
+
+// ---- dgemm.cu : generic SIMT FP64 GEMM (tall-skinny shapes, deterministic split-K) -------------
+// C(M x N, ldc) = alpha * op(A) * B(K x N, ldb) + beta * C
+//   transA == false : A is M x K (lda)            -- "NN": V*G updates, AV*Y, C*T
+//   transA == true  : A is stored K x M (lda)     -- "TN": projections V^T W (K = local rows)
+// ws: workspace for split-K partials (TN with long K); ws_doubles its capacity.
+void gemm(cudaStream_t s, bool transA, int64_t M, int64_t N, int64_t K, double alpha, const double* A,
+          int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, double* ws,
+          size_t ws_doubles);
+
+// ---- matvec_dmma.cu : the hot kernel.  W(M x b) = A(M x K, lda) * X(K x b)  ---------------------
+// TMA (2D tensor map, 128B swizzle) -> mbarrier pipeline -> FP64 DMMA, persistent stream-K grid.
+struct MatvecPlan;  // opaque: tensor map + workspace for one resident matrix
+MatvecPlan* matvec_plan_create(const double* A, int64_t M, int64_t K, int64_t lda, int max_b);
+void matvec_plan_destroy(MatvecPlan* p);
+bool matvec_dmma_supported();
+// X is K x b column-major (ldx); Xp is scratch for the packed copy of X (>= round_up(K,64)*round_up(b,8)).
+void matvec_dmma(cudaStream_t s, MatvecPlan* plan, int b, const double* X, int64_t ldx, double* W, int64_t ldw);
+
+// ---- freeops.cu : on-the-fly operators (benchmark_free.f90:38-76, tests/test_utils.f90:37-116) --
+// W(rows row0..row0+nl) = Op * X(n x b); etab[n] = (double)expf(i/n) table (built on host with glibc expf).
+void free_matmul_builtin(cudaStream_t s, int op, int64_t n, int64_t row0, int64_t nl, int b, const double* etab,
+                         const double* X, int64_t ldx, double* W, int64_t ldw);
+void free_diag_builtin(cudaStream_t s, int op, int64_t n, int64_t row0, int64_t nl, const double* etab,
+                       double* diag);
+void free_column_builtin(cudaStream_t s, int op, int64_t n, int64_t col /*0-based*/, const double* etab,
+                         double* out);
+
+// ---- smalldense.cu : k x k problems on one CTA ----------------------------------------------------
+// Two-sided Jacobi, round-robin parallel ordering.  S: k x k (ld k), upper triangle read, destroyed.
+// Y: k x k eigenvectors sorted by ascending eigenvalue w.  status: device int, set nonzero on failure
+// (1 = no convergence / NaN).  scratch: >= 2*(k+1)^2 doubles of global memory.
+void jacobi_eigh(cudaStream_t s, int k, double* S, double* Y, double* w, double* scratch, int* status);
+// T(:,j) = U(:,j) / sqrt(sv[j]); status |= 2 if some sv[j] <= 0 (not positive definite)
+void scale_cols_rsqrt_checked(cudaStream_t s, int k, const double* U, const double* sv, double* T, int* status);
+// D = diag(G)^-1/2 (0 where diag <= 0); G <- D G D
+void gram_prescale(cudaStream_t s, int k, double* G, double* D);
+// SVQB transform: T(i,j) = D[i] * U(i,j) / sqrt(sv[j]) for sv[j] > thr*max(sv), else column flagged
+// deficient (flags[j] = 1, T(:,j) = 0).
+void svqb_make_T(cudaStream_t s, int k, const double* U, const double* sv, const double* D, double* T,
+                 int* flags);
+// lower triangle <- upper triangle of the k x k matrix (ld)
+void symmetrize_from_upper(cudaStream_t s, int k, double* S, int64_t ld);
+// max |G - (minus_identity ? I : 0)| over the rows x cols matrix -> out[0] (single CTA; NaN -> 1e300)
+void max_abs_dev(cudaStream_t s, int rows, int cols, const double* G, int64_t ld, bool minus_identity, double* out);
+// Cholesky (upper, G = R^T R) in place on one CTA; status |= 2 when not positive definite
+void cholesky_upper(cudaStream_t s, int k, double* G, int64_t ld, int* status);
+// Rinv = inverse of the upper triangular R (k x k)
+void invert_upper(cudaStream_t s, int k, const double* R, int64_t ld, double* Rinv);
+
+// ---- vecops.cu : n x k vector-block kernels and generators --------------------------------------
+void fill_zero(cudaStream_t s, double* p, size_t count);
+void copy_matrix(cudaStream_t s, int64_t rows, int64_t cols, const double* src, int64_t lds, double* dst,
+                 int64_t ldd);
+// dst(k x k, ldd)[r0.., c0..] block copies used for the projected matrices
+void gen_diag_dominant(cudaStream_t s, double* A, int64_t lda, int64_t nl, int64_t n, int64_t row0, double sparsity,
+                       int has_diag, double diag_val, uint64_t seed);
+void extract_diag(cudaStream_t s, const double* A, int64_t lda, int64_t nl, int64_t row0, double* out);
+// (value,index) of the `k` smallest entries of diag[0..nl) (global index = row0 + i), ascending,
+// ties by index.  Single CTA.  status |= 1 on NaN.
+void topk_smallest(cudaStream_t s, const double* diag, const int64_t* gidx /*nullable*/, int64_t count,
+                   int64_t row0, int k, double* out_val, int64_t* out_idx, int* status);
+// V(nl x k) one-hot: V(idx[j]-row0, j) = 1 when idx[j] is a local row
+void set_onehot(cudaStream_t s, double* V, int64_t ldv, int64_t nl, int64_t row0, const int64_t* idx, int k);
+// out(:, j) = A(:, idx[j])   (A is nl x n local row block)
+void gather_columns(cudaStream_t s, const double* A, int64_t lda, int64_t nl, const int64_t* idx, int k,
+                    double* out, int64_t ldo);
+// out(nl x k) = diag(d) applied to one-hot columns: out(i,j) = (row0+i == idx[j]) ? d[i] : 0  (unused for dense)
+// squared column norms, deterministic two-stage; partial: >= k*256 doubles
+void col_norms2(cudaStream_t s, int64_t nl, int k, const double* X, int64_t ldx, double* partial, double* out);
+// X(:,j) *= 1/sqrt(n2[j]) when n2[j] > 0
+void scale_cols_rsqrt(cudaStream_t s, int64_t nl, int k, double* X, int64_t ldx, const double* n2);
+// residual + DPR (davidson.f90:163-170 via stored products, :688-696; free :401-410, :484):
+//   r = R - theta_j * C ; R <- r ; C <- r / (theta_j * dB_i - dA_i)   (dB == nullptr -> 1)
+//   n2part: partial squared norms of r (deterministic two-stage, as col_norms2)
+void residual_dpr(cudaStream_t s, int64_t nl, int k, double* R, int64_t ldr, double* C, int64_t ldc,
+                  const double* theta, const double* dA, const double* dB, bool write_correction, double* partial,
+                  double* n2out);
+// pseudo-random refill of flagged columns (rank-deficient directions of an expansion block)
+void fill_random_cols(cudaStream_t s, double* X, int64_t ldx, int64_t nl, int64_t row0, const int* flags, int k,
+                      uint64_t salt);
+// deterministic pseudo-random block in [-1,1) (bench input)
+void fill_random(cudaStream_t s, double* X, size_t count, uint64_t salt);
+// staged all-gather layout [rank][chunk x b] -> column-major n x b
+void unstage_allgather(cudaStream_t s, const double* stage, int world, int64_t chunk, int64_t n, int b, double* X,
+                       int64_t ldx);
+// column-major nl x b (ldx) -> contiguous chunk x b (zero padded rows)
+void stage_block(cudaStream_t s, const double* X, int64_t ldx, int64_t nl, int64_t chunk, int b, double* stage);
+
+}  // namespace dav

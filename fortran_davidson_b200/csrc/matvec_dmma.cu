@@ -1,0 +1,424 @@
+// The hot kernel: block matvec  W(M x b) = A(M x K, lda) * X(K x b)  in FP64, A streamed from HBM
+// exactly once for all b columns.  Replaces the reference's DGEMM A*V / B*V (davidson.f90:131,134,
+// 223,226 via lapack_wrapper.f90:279-328) and, through the stored products, its k DGEMVs per
+// iteration (davidson.f90:163-170).
+//
+// sm_100a design
+//   * persistent grid, one CTA per SM, stream-K: the (row tile x k step) units are split evenly and
+//     contiguously over the CTAs; partially covered tiles go to a workspace and a tiny fixup kernel
+//     adds them in a fixed order (bit-reproducible, no atomics).
+//   * warp-specialised: warp 8 is the TMA producer, warps 0-7 consume.  A tiles arrive through a
+//     2D tensor map (box 16 rows x 16 columns, 128-byte swizzle) with mbarrier complete_tx; the X
+//     tile is pre-packed in fragment order so one 1D bulk copy per stage fetches it.
+//   * FP64 tensor-core math: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4).  tcgen05 has no FP64 kind, so
+//     TMEM / UTCMMA do not apply to this path.
+//   * shared-memory fragment loads are 128-bit and bank-conflict free: the 128B swizzle puts rows
+//     (2g, 2g+1) of column k at chunk g ^ (k & 7); a lane (g, t) reads column k0 + 2t + o, so the 8
+//     lanes of a quarter warp hit 8 distinct chunks of 4 distinct lines.
+//
+// Algorithmic traffic per launch: 8*M*K (A) + 8*K*b (X) + 8*M*b (W) bytes; 2*M*K*b flops.
+#include <cuda.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace dav {
+
+namespace {
+
+constexpr int BK = 16;            // k columns per pipeline stage
+constexpr int CONSUMERS = 8;      // consumer warps
+constexpr int THREADS = (CONSUMERS + 1) * 32;
+constexpr int MAX_STAGES = 8;
+constexpr int NUM_SMS_FALLBACK = 148;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double2 lds128(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+
+struct Params {
+  int64_t M, K;        // rows of the local block, columns (= global n)
+  int b;               // real column count (<= bpad)
+  int tiles, ksteps;   // row tiles, k steps
+  long long total;     // tiles * ksteps
+  long long quota;     // units per CTA
+  int stages;
+  const double* Xp;    // packed X: [kstep][BK x bpad] in fragment order
+  double* W;
+  int64_t ldw;
+  double* ws;          // partial tiles: [cta][2][BM x bpad]
+};
+
+// X packed index of element (k, j): ((k/8 * NTT + j/8) * 64 + (j%8)*8 + k%8)
+__global__ void pack_x_kernel(int64_t K, int64_t Kpad, int b, int bpad, const double* __restrict__ X, int64_t ldx,
+                              double* __restrict__ Xp) {
+  const int ntt = bpad / 8;
+  const int64_t total = Kpad * bpad;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    // e enumerates the packed layout so that stores are coalesced
+    const int kk = (int)(e & 7);
+    const int g = (int)((e >> 3) & 7);
+    const int64_t blk = e >> 6;
+    const int jt = (int)(blk % ntt);
+    const int64_t kq = blk / ntt;
+    const int64_t k = kq * 8 + kk;
+    const int j = jt * 8 + g;
+    Xp[e] = (k < K && j < b) ? X[k + (int64_t)j * ldx] : 0.0;
+  }
+}
+
+template <int NT, int WARPS_N>
+__global__ void __maxnreg__(224)
+    matvec_kernel(const __grid_constant__ CUtensorMap tmapA, const Params p) {
+  constexpr int WARPS_M = CONSUMERS / WARPS_N;
+  constexpr int BM = WARPS_M * 32;
+  constexpr int NTT = NT * WARPS_N;          // 8-column tiles of the CTA tile
+  constexpr int BPAD = NTT * 8;
+  constexpr uint32_t A_BYTES = BM * BK * 8;  // per stage
+  constexpr uint32_t X_BYTES = BK * BPAD * 8;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + X_BYTES;
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.stages;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), CONSUMERS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const long long u_begin = (long long)blockIdx.x * p.quota;
+  const long long u_end = min(p.total, u_begin + p.quota);
+  if (u_begin >= u_end) return;
+
+  if (warp == CONSUMERS) {
+    // ================= TMA producer (one elected lane) =================
+    if (lane == 0) {
+      long long it = 0;
+      for (long long u = u_begin; u < u_end; ++u, ++it) {
+        const int s = (int)(it % S);
+        const uint32_t ph = (uint32_t)((it / S) & 1);
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+        const int tile = (int)(u / p.ksteps), ks = (int)(u % p.ksteps);
+        const uint32_t fb = smem_u32(&full_bar[s]);
+        mbar_expect_tx(fb, STAGE_BYTES);
+        const uint32_t a_dst = base + (uint32_t)s * STAGE_BYTES;
+#pragma unroll
+        for (int rg = 0; rg < BM / 16; ++rg)
+          tma_load_2d(a_dst + rg * (BK * 128), &tmapA, tile * BM + rg * 16, ks * BK, fb);
+        bulk_load_1d(a_dst + A_BYTES, p.Xp + (size_t)ks * (BK * BPAD), X_BYTES, fb);
+      }
+    }
+    return;
+  }
+
+  // ================= consumers =================
+  const int wr = warp / WARPS_N, wc = warp % WARPS_N;
+  const int g = lane >> 2, t = lane & 3;
+  double acc[2][2][NT][2];  // [row group][even/odd row][col tile][c0,c1]
+
+  // per-lane byte offsets inside a stage
+  // A: sub-tile (wr*2 + rg) * (BK*128) + kk*128 + ((g ^ (kk&7)) << 4), kk = 8q + 2t + o
+  // X: A_BYTES + ((q*NTT + wc*NT + nt)*64 + g*8 + 2t) * 8
+  const uint32_t a_lane = (uint32_t)(wr * 2) * (BK * 128);
+  const uint32_t x_lane = A_BYTES + (uint32_t)((wc * NT) * 64 + g * 8 + 2 * t) * 8;
+
+  long long it = 0;
+  long long u = u_begin;
+  while (u < u_end) {
+    // one segment = consecutive k steps of one row tile
+    const int tile = (int)(u / p.ksteps);
+    const int ks0 = (int)(u - (long long)tile * p.ksteps);
+    const int ks1 = (int)min((long long)p.ksteps, (long long)ks0 + (u_end - u));
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+#pragma unroll
+        for (int n = 0; n < NT; ++n) acc[a][e][n][0] = acc[a][e][n][1] = 0.0;
+
+    for (int ks = ks0; ks < ks1; ++ks, ++it) {
+      const int s = (int)(it % S);
+      const uint32_t ph = (uint32_t)((it / S) & 1);
+      mbar_wait(smem_u32(&full_bar[s]), ph);
+      const uint32_t sb = base + (uint32_t)s * STAGE_BYTES;
+#pragma unroll
+      for (int q = 0; q < BK / 8; ++q) {
+        double2 xf[NT];
+#pragma unroll
+        for (int n = 0; n < NT; ++n) xf[n] = lds128(sb + x_lane + (uint32_t)((q * NTT + n) * 64) * 8);
+#pragma unroll
+        for (int rg = 0; rg < 2; ++rg) {
+#pragma unroll
+          for (int o = 0; o < 2; ++o) {
+            const int kk = 8 * q + 2 * t + o;
+            const double2 af = lds128(sb + a_lane + (uint32_t)rg * (BK * 128) + (uint32_t)kk * 128 +
+                                      (uint32_t)((g ^ (kk & 7)) << 4));
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+              const double xv = o ? xf[n].y : xf[n].x;
+              dmma(acc[rg][0][n][0], acc[rg][0][n][1], af.x, xv);
+              dmma(acc[rg][1][n][0], acc[rg][1][n][1], af.y, xv);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&empty_bar[s]));
+    }
+
+    const bool complete = (ks0 == 0) && (ks1 == p.ksteps);
+    if (complete) {
+      const int64_t row_base = (int64_t)tile * BM + wr * 32;
+#pragma unroll
+      for (int rg = 0; rg < 2; ++rg)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int64_t row = row_base + rg * 16 + 2 * g + e;
+          if (row < p.M) {
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+              const int j = (wc * NT + n) * 8 + 2 * t;
+              if (j < p.b) p.W[row + (int64_t)j * p.ldw] = acc[rg][e][n][0];
+              if (j + 1 < p.b) p.W[row + (int64_t)(j + 1) * p.ldw] = acc[rg][e][n][1];
+            }
+          }
+        }
+    } else {
+      // partial tile -> workspace slot (0: the CTA's first segment, 1: a later one)
+      const int slot = (u == u_begin) ? 0 : 1;
+      double* w = p.ws + ((size_t)blockIdx.x * 2 + slot) * (size_t)(BM * BPAD);
+#pragma unroll
+      for (int rg = 0; rg < 2; ++rg)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int r = wr * 32 + rg * 16 + 2 * g + e;
+#pragma unroll
+          for (int n = 0; n < NT; ++n) {
+            const int j = (wc * NT + n) * 8 + 2 * t;
+            w[r + j * BM] = acc[rg][e][n][0];
+            w[r + (j + 1) * BM] = acc[rg][e][n][1];
+          }
+        }
+    }
+    u += ks1 - ks0;
+  }
+}
+
+// Adds the partial tiles of every row tile that was split over several CTAs, in CTA order.
+__global__ void fixup_kernel(int BM, int BPAD, Params p) {
+  const int tile = blockIdx.x;
+  const long long u0 = (long long)tile * p.ksteps, u1 = u0 + p.ksteps;
+  const int cA = (int)(u0 / p.quota), cB = (int)((u1 - 1) / p.quota);
+  if (cA == cB) return;  // written directly
+  const int elems = BM * BPAD;
+  for (int e = threadIdx.x; e < elems; e += blockDim.x) {
+    const int r = e % BM, j = e / BM;
+    const int64_t row = (int64_t)tile * BM + r;
+    if (row >= p.M || j >= p.b) continue;
+    double s = 0.0;
+    for (int c = cA; c <= cB; ++c) {
+      const int slot = ((long long)c * p.quota >= u0) ? 0 : 1;
+      s += p.ws[((size_t)c * 2 + slot) * (size_t)elems + e];
+    }
+    p.W[row + (int64_t)j * p.ldw] = s;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+    else
+      (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+template <int NT, int WARPS_N>
+void launch_cfg(cudaStream_t s, const CUtensorMap& map, Params& p, int max_smem, int num_sms, double* ws,
+                size_t ws_doubles) {
+  constexpr int BM = (CONSUMERS / WARPS_N) * 32;
+  constexpr int BPAD = NT * WARPS_N * 8;
+  constexpr int STAGE_BYTES = BM * BK * 8 + BK * BPAD * 8;
+  p.tiles = (int)ceil_div(p.M, BM);
+  p.total = (long long)p.tiles * p.ksteps;
+  int grid = (int)std::min<long long>(num_sms, p.total);
+  const size_t slot = (size_t)BM * BPAD;
+  if ((size_t)grid * 2 * slot > ws_doubles) grid = (int)std::max<size_t>(1, ws_doubles / (2 * slot));
+  p.quota = (p.total + grid - 1) / grid;
+  grid = (int)((p.total + p.quota - 1) / p.quota);
+  p.stages = std::min(MAX_STAGES, (max_smem - 1024 - 256) / STAGE_BYTES);
+  if (p.stages < 2) DAV_THROW(DAV_ERR_CUDA, "not enough shared memory for the matvec pipeline");
+  p.ws = ws;
+  const size_t smem = (size_t)p.stages * STAGE_BYTES + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(matvec_kernel<NT, WARPS_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 256));
+    attr_set = true;
+  }
+  matvec_kernel<NT, WARPS_N><<<grid, THREADS, smem, s>>>(map, p);
+  CK_LAUNCH();
+  ++g_kernel_launches;
+  fixup_kernel<<<p.tiles, 256, 0, s>>>(BM, BPAD, p);
+  CK_LAUNCH();
+  ++g_kernel_launches;
+}
+
+}  // namespace
+
+struct MatvecPlan {
+  CUtensorMap map;
+  const double* A;
+  int64_t M, K, lda;
+  int max_b;
+  DevBuf<double> Xp, ws;
+  int max_smem, num_sms;
+};
+
+bool matvec_dmma_supported() { return get_encode_fn() != nullptr; }
+
+MatvecPlan* matvec_plan_create(const double* A, int64_t M, int64_t K, int64_t lda, int max_b) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) DAV_THROW(DAV_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  if ((lda * 8) % 16 != 0 || ((uintptr_t)A & 15) != 0)
+    DAV_THROW(DAV_ERR_INVALID, "matvec: matrix block must be 16-byte aligned with an even leading dimension");
+  MatvecPlan* p = new MatvecPlan();
+  p->A = A; p->M = M; p->K = K; p->lda = lda; p->max_b = max_b;
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  CK(cudaDeviceGetAttribute(&p->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  CK(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev));
+  if (p->num_sms <= 0) p->num_sms = NUM_SMS_FALLBACK;
+  cuuint64_t gdim[2] = {(cuuint64_t)M, (cuuint64_t)K};
+  cuuint64_t gstride[1] = {(cuuint64_t)lda * 8};
+  cuuint32_t box[2] = {16, (cuuint32_t)BK};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(&p->map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)A, gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    delete p;
+    DAV_THROW(DAV_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  }
+  const int bmax = (int)std::min<int64_t>(round_up(std::max(max_b, 8), 8), 128);
+  p->Xp.alloc((size_t)round_up(K, BK) * bmax);
+  p->ws.alloc((size_t)p->num_sms * 2 * 256 * 64);
+  return p;
+}
+
+void matvec_plan_destroy(MatvecPlan* p) { delete p; }
+
+void matvec_dmma(cudaStream_t s, MatvecPlan* plan, int b, const double* X, int64_t ldx, double* W, int64_t ldw) {
+  if (b <= 0 || plan->M <= 0) return;
+  const int64_t Kpad = round_up(plan->K, BK);
+  for (int j0 = 0; j0 < b; j0 += 128) {
+    const int bc = std::min(128, b - j0);
+    int bpad = (int)round_up(bc, 8);
+    // config: one column warp up to 64 columns, two above
+    int warps_n = bpad <= 64 ? 1 : 2;
+    int nt = warps_n == 1 ? bpad / 8 : (bpad + 15) / 16;
+    bpad = nt * warps_n * 8;
+    if ((size_t)Kpad * bpad > plan->Xp.n) plan->Xp.alloc((size_t)Kpad * bpad);
+    {
+      const int64_t total = Kpad * bpad;
+      const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 1184);
+      pack_x_kernel<<<blocks, 256, 0, s>>>(plan->K, Kpad, bc, bpad, X + (int64_t)j0 * ldx, ldx, plan->Xp.p);
+      CK_LAUNCH();
+      ++g_kernel_launches;
+    }
+    Params p;
+    p.M = plan->M; p.K = plan->K; p.b = bc;
+    p.ksteps = (int)(Kpad / BK);
+    p.Xp = plan->Xp.p;
+    p.W = W + (int64_t)j0 * ldw;
+    p.ldw = ldw;
+#define CFG(NT_, WN_)                                                                                      \
+  launch_cfg<NT_, WN_>(s, plan->map, p, plan->max_smem, plan->num_sms, plan->ws.p, plan->ws.n)
+    if (warps_n == 1) {
+      switch (nt) {
+        case 1: CFG(1, 1); break;
+        case 2: CFG(2, 1); break;
+        case 3: CFG(3, 1); break;
+        case 4: CFG(4, 1); break;
+        case 5: CFG(5, 1); break;
+        case 6: CFG(6, 1); break;
+        case 7: CFG(7, 1); break;
+        default: CFG(8, 1); break;
+      }
+    } else {
+      switch (nt) {
+        case 5: CFG(5, 2); break;
+        case 6: CFG(6, 2); break;
+        case 7: CFG(7, 2); break;
+        default: CFG(8, 2); break;
+      }
+    }
+#undef CFG
+  }
+}
+
+}  // namespace dav

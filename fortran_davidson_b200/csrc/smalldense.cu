@@ -1,0 +1,359 @@
+// Small dense (k x k) problems, each solved by ONE CTA: replaces lapack_wrapper.f90's DSYEV /
+// DSYGV call sites of the Rayleigh-Ritz step (lapack_wrapper.f90:14-91; davidson.f90:153,155,394)
+// and supplies the Gram-matrix transforms of the block orthonormalisation that replaces
+// DGEQRF+DORGQR (lapack_wrapper.f90:176-236; davidson.f90:213,434).
+//
+// jacobi_eigh: two-sided Jacobi with the round-robin ("chess tournament") parallel ordering:
+// each round rotates k/2 disjoint (p,q) pairs; a thread owns one 2x2 block S[{p1,q1},{p2,q2}] and
+// applies J_P^T . J_Q to it, so a round needs two block barriers and no atomics.  S lives in
+// shared memory whenever it fits (k <= ~165), the eigenvector accumulator too when both fit
+// (k <= ~117); otherwise they stay in L2-resident global scratch.
+#include <algorithm>
+
+#include "kernels.cuh"
+
+namespace dav {
+namespace {
+
+constexpr double EPS = 2.220446049250313e-16;
+constexpr int JT = 1024;      // threads of the Jacobi CTA
+constexpr int MAX_SWEEPS = 40;
+
+__device__ __forceinline__ double block_reduce_sum(double v, double* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    double x = (lane < (blockDim.x + 31) / 32) ? red[lane] : 0.0;
+    x = warp_sum(x);
+    if (lane == 0) red[0] = x;
+  }
+  __syncthreads();
+  const double r = red[0];
+  __syncthreads();
+  return r;
+}
+
+__device__ __forceinline__ double block_reduce_max(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    double x = (lane < (blockDim.x + 31) / 32) ? red[lane] : -1.0e300;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+    if (lane == 0) red[0] = x;
+  }
+  __syncthreads();
+  const double r = red[0];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(JT) jacobi_kernel(int k, const double* __restrict__ S_in, double* __restrict__ Y,
+                                                    double* __restrict__ w, double* gS, double* gV, int s_in_smem,
+                                                    int v_in_smem, int* status) {
+  extern __shared__ __align__(16) double sm[];
+  const int kp = k + (k & 1), np = kp / 2;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  // carve shared memory: small arrays first, then the big ones
+  double* red = sm;                      // 32
+  double* rc = red + 32;                 // np
+  double* rs = rc + np;                  // np
+  double* wv = rs + np;                  // kp
+  int* rp = reinterpret_cast<int*>(wv + kp);  // np
+  int* rq = rp + np;                          // np
+  int* rk = rq + np;                          // kp
+  size_t off = 32 + 2 * (size_t)np + kp + ((2 * (size_t)np + kp) * sizeof(int) + 7) / 8;
+  off = (off + 1) & ~(size_t)1;
+  double* S = gS;
+  double* V = gV;
+  if (s_in_smem) { S = sm + off; off += (size_t)kp * kp; }
+  if (v_in_smem) { V = sm + off; }
+
+  // 1. symmetrise from the upper triangle (DSYEV 'U'), V = I
+  double part = 0.0;
+  for (int e = tid; e < kp * kp; e += nt) {
+    const int i = e % kp, j = e / kp;
+    double v = 0.0;
+    if (i < k && j < k) v = (i <= j) ? S_in[i + (size_t)j * k] : S_in[j + (size_t)i * k];
+    S[e] = v;
+    V[e] = (i == j) ? 1.0 : 0.0;
+    part += v * v;
+  }
+  const double normF = sqrt(block_reduce_sum(part, red));
+  if (!(normF <= 1.0e300)) {  // NaN or Inf in the input
+    if (tid == 0) atomicOr(status, 1);
+    return;
+  }
+  const double abs_thr = EPS * normF / (16.0 * kp);
+
+  // 2. sweeps
+  const int m = kp - 1;
+  for (int sweep = 0; sweep < MAX_SWEEPS; ++sweep) {
+    int rotated = 0;
+    for (int r = 0; r < m; ++r) {
+      if (tid < np) {
+        int a, b;
+        if (tid == 0) { a = kp - 1; b = r; }
+        else { a = (r + tid) % m; b = (r - tid + m) % m; }
+        const int p = min(a, b), q = max(a, b);
+        double c = 1.0, s = 0.0;
+        if (q < k) {
+          const double apq = S[p + (size_t)q * kp], app = S[p + (size_t)p * kp], aqq = S[q + (size_t)q * kp];
+          const double aa = fabs(apq);
+          if (aa > abs_thr && aa > EPS * sqrt(fabs(app) * fabs(aqq))) {
+            const double tau = (aqq - app) / (2.0 * apq);
+            const double t = copysign(1.0, tau) / (fabs(tau) + sqrt(1.0 + tau * tau));
+            c = 1.0 / sqrt(1.0 + t * t);
+            s = t * c;
+            rotated = 1;
+          }
+        }
+        rc[tid] = c; rs[tid] = s; rp[tid] = p; rq[tid] = q;
+      }
+      __syncthreads();
+      // S <- J^T S J, one 2x2 block per work item (upper block-triangle, mirrored)
+      for (int e = tid; e < np * np; e += nt) {
+        const int iP = e % np, iQ = e / np;
+        if (iP > iQ) continue;
+        const double cP = rc[iP], sP = rs[iP], cQ = rc[iQ], sQ = rs[iQ];
+        if (sP == 0.0 && sQ == 0.0) continue;
+        const int p1 = rp[iP], q1 = rq[iP], p2 = rp[iQ], q2 = rq[iQ];
+        if (iP == iQ) {
+          const double apq = S[p1 + (size_t)q1 * kp], app = S[p1 + (size_t)p1 * kp], aqq = S[q1 + (size_t)q1 * kp];
+          const double t = sP / cP;
+          S[p1 + (size_t)p1 * kp] = app - t * apq;
+          S[q1 + (size_t)q1 * kp] = aqq + t * apq;
+          S[p1 + (size_t)q1 * kp] = 0.0;
+          S[q1 + (size_t)p1 * kp] = 0.0;
+        } else {
+          const double m00 = S[p1 + (size_t)p2 * kp], m01 = S[p1 + (size_t)q2 * kp];
+          const double m10 = S[q1 + (size_t)p2 * kp], m11 = S[q1 + (size_t)q2 * kp];
+          const double r00 = cP * m00 - sP * m10, r01 = cP * m01 - sP * m11;
+          const double r10 = sP * m00 + cP * m10, r11 = sP * m01 + cP * m11;
+          const double n00 = cQ * r00 - sQ * r01, n01 = sQ * r00 + cQ * r01;
+          const double n10 = cQ * r10 - sQ * r11, n11 = sQ * r10 + cQ * r11;
+          S[p1 + (size_t)p2 * kp] = n00; S[p2 + (size_t)p1 * kp] = n00;
+          S[p1 + (size_t)q2 * kp] = n01; S[q2 + (size_t)p1 * kp] = n01;
+          S[q1 + (size_t)p2 * kp] = n10; S[p2 + (size_t)q1 * kp] = n10;
+          S[q1 + (size_t)q2 * kp] = n11; S[q2 + (size_t)q1 * kp] = n11;
+        }
+      }
+      // V <- V J
+      for (int e = tid; e < kp * np; e += nt) {
+        const int row = e % kp, iP = e / kp;
+        const double s = rs[iP];
+        if (s == 0.0) continue;
+        const double c = rc[iP];
+        const int p = rp[iP], q = rq[iP];
+        const double vp = V[row + (size_t)p * kp], vq = V[row + (size_t)q * kp];
+        V[row + (size_t)p * kp] = c * vp - s * vq;
+        V[row + (size_t)q * kp] = s * vp + c * vq;
+      }
+      __syncthreads();
+    }
+    const int any = __syncthreads_or(rotated);
+    if (!any) break;
+    if (sweep == MAX_SWEEPS - 1 && tid == 0) atomicOr(status, 1);
+  }
+
+  // 3. ascending order (stable), scatter eigenvectors
+  for (int i = tid; i < k; i += nt) wv[i] = S[i + (size_t)i * kp];
+  __syncthreads();
+  for (int i = tid; i < k; i += nt) {
+    const double wi = wv[i];
+    int rank = 0;
+    for (int j = 0; j < k; ++j) {
+      const double wj = wv[j];
+      rank += (wj < wi) || (wj == wi && j < i);
+    }
+    if (!(wi == wi)) { atomicOr(status, 1); rank = i; }
+    rk[i] = rank;
+    w[rank] = wi;
+  }
+  __syncthreads();
+  for (int e = tid; e < k * k; e += nt) {
+    const int row = e % k, col = e / k;
+    Y[row + (size_t)rk[col] * k] = V[row + (size_t)col * kp];
+  }
+}
+
+__global__ void scale_cols_rsqrt_checked_kernel(int k, const double* __restrict__ U, const double* __restrict__ sv,
+                                                double* __restrict__ T, int* status) {
+  for (int e = threadIdx.x; e < k * k; e += blockDim.x) {
+    const int j = e / k;
+    const double s = sv[j];
+    if (!(s > 0.0)) {
+      if (e % k == 0) atomicOr(status, 2);
+      T[e] = 0.0;
+    } else {
+      T[e] = U[e] / sqrt(s);
+    }
+  }
+}
+
+__global__ void gram_prescale_kernel(int k, double* G, double* D) {
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    const double d = G[i + (size_t)i * k];
+    D[i] = (d > 0.0) ? 1.0 / sqrt(d) : 0.0;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < k * k; e += blockDim.x) G[e] *= D[e % k] * D[e / k];
+}
+
+__global__ void svqb_make_T_kernel(int k, const double* __restrict__ U, const double* __restrict__ sv,
+                                   const double* __restrict__ D, double* __restrict__ T, int* flags) {
+  __shared__ double red[32];
+  double mx = -1.0e300;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) mx = fmax(mx, sv[j]);
+  const double smax = block_reduce_max(mx, red);
+  const double thr = smax * (double)k * EPS * 16.0;
+  for (int e = threadIdx.x; e < k * k; e += blockDim.x) {
+    const int i = e % k, j = e / k;
+    const double s = sv[j];
+    const bool good = (smax > 0.0) && (s > thr);
+    T[e] = good ? D[i] * U[e] / sqrt(s) : 0.0;
+    if (i == 0) flags[j] = good ? 0 : 1;
+  }
+}
+
+__global__ void symmetrize_from_upper_kernel(int k, double* S, int64_t ld) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < k * k; e += gridDim.x * blockDim.x) {
+    const int i = e % k, j = e / k;
+    if (i > j) S[i + j * ld] = S[j + i * ld];
+  }
+}
+
+__global__ void max_abs_kernel(int rows, int cols, const double* __restrict__ G, int64_t ld, int minus_identity,
+                               double* out) {
+  __shared__ double red[32];
+  double mx = 0.0;
+  for (int e = threadIdx.x; e < rows * cols; e += blockDim.x) {
+    const int i = e % rows, j = e / rows;
+    const double v = fabs(G[i + j * ld] - ((minus_identity && i == j) ? 1.0 : 0.0));
+    mx = (v == v) ? fmax(mx, v) : 1.0e300;
+  }
+  const double r = block_reduce_max(mx, red);
+  if (threadIdx.x == 0) out[0] = r;
+}
+
+__global__ void __launch_bounds__(1024) cholesky_upper_kernel(int k, double* G, int64_t ld, int* status) {
+  __shared__ double piv;
+  __shared__ int bad;
+  if (threadIdx.x == 0) bad = 0;
+  __syncthreads();
+  for (int j = 0; j < k; ++j) {
+    if (threadIdx.x == 0) {
+      const double d = G[j + (size_t)j * ld];
+      if (!(d > 0.0)) { bad = 1; piv = 1.0; }
+      else piv = sqrt(d);
+      G[j + (size_t)j * ld] = piv;
+    }
+    __syncthreads();
+    if (bad) break;
+    const double r = piv;
+    for (int i = j + 1 + threadIdx.x; i < k; i += blockDim.x) G[j + (size_t)i * ld] /= r;
+    __syncthreads();
+    const int rem = k - j - 1;
+    for (int e = threadIdx.x; e < rem * rem; e += blockDim.x) {
+      const int a = j + 1 + e % rem, b = j + 1 + e / rem;
+      if (a <= b) G[a + (size_t)b * ld] -= G[j + (size_t)a * ld] * G[j + (size_t)b * ld];
+    }
+    __syncthreads();
+  }
+  if (bad && threadIdx.x == 0) atomicOr(status, 2);
+  // zero the strict lower triangle so the result is a clean R
+  for (int e = threadIdx.x; e < k * k; e += blockDim.x) {
+    const int i = e % k, j = e / k;
+    if (i > j) G[i + (size_t)j * ld] = 0.0;
+  }
+}
+
+__global__ void invert_upper_kernel(int k, const double* __restrict__ R, int64_t ld, double* __restrict__ X) {
+  // column j of X solves R x = e_j (x_i = 0 for i > j), back substitution
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < k; j += gridDim.x * blockDim.x) {
+    double* x = X + (size_t)j * k;
+    for (int i = k - 1; i > j; --i) x[i] = 0.0;
+    for (int i = j; i >= 0; --i) {
+      double s = (i == j) ? 1.0 : 0.0;
+      for (int l = i + 1; l <= j; ++l) s -= R[i + (size_t)l * ld] * x[l];
+      x[i] = s / R[i + (size_t)i * ld];
+    }
+  }
+}
+
+}  // namespace
+
+void jacobi_eigh(cudaStream_t s, int k, double* S, double* Y, double* w, double* scratch, int* status) {
+  if (k <= 0) return;
+  const int kp = k + (k & 1), np = kp / 2;
+  size_t small = 32 + 2 * (size_t)np + kp + ((2 * (size_t)np + kp) * sizeof(int) + 7) / 8;
+  small = (small + 1) & ~(size_t)1;
+  const size_t big = (size_t)kp * kp;
+  static int max_smem = -1;
+  if (max_smem < 0) {
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    CK(cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  }
+  const size_t cap = (size_t)max_smem / sizeof(double);
+  int s_in = 0, v_in = 0;
+  size_t doubles = small;
+  if (small + 2 * big <= cap) { s_in = 1; v_in = 1; doubles += 2 * big; }
+  else if (small + big <= cap) { s_in = 1; doubles += big; }
+  jacobi_kernel<<<1, JT, doubles * sizeof(double), s>>>(k, S, Y, w, scratch, scratch + big, s_in, v_in, status);
+  CK_LAUNCH();
+  ++g_kernel_launches;
+}
+
+void scale_cols_rsqrt_checked(cudaStream_t s, int k, const double* U, const double* sv, double* T, int* status) {
+  scale_cols_rsqrt_checked_kernel<<<1, 1024, 0, s>>>(k, U, sv, T, status);
+  CK_LAUNCH();
+  ++g_kernel_launches;
+}
+
+void gram_prescale(cudaStream_t s, int k, double* G, double* D) {
+  gram_prescale_kernel<<<1, 1024, 0, s>>>(k, G, D);
+  CK_LAUNCH();
+  ++g_kernel_launches;
+}
+
+void svqb_make_T(cudaStream_t s, int k, const double* U, const double* sv, const double* D, double* T, int* flags) {
+  svqb_make_T_kernel<<<1, 1024, 0, s>>>(k, U, sv, D, T, flags);
+  CK_LAUNCH();
+  ++g_kernel_launches;
+}
+
+void symmetrize_from_upper(cudaStream_t s, int k, double* S, int64_t ld) {
+  const int blocks = std::max(1, std::min(64, (k * k + 255) / 256));
+  symmetrize_from_upper_kernel<<<blocks, 256, 0, s>>>(k, S, ld);
+  CK_LAUNCH();
+  ++g_kernel_launches;
+}
+
+void max_abs_dev(cudaStream_t s, int rows, int cols, const double* G, int64_t ld, bool minus_identity, double* out) {
+  max_abs_kernel<<<1, 1024, 0, s>>>(rows, cols, G, ld, minus_identity ? 1 : 0, out);
+  CK_LAUNCH();
+  ++g_kernel_launches;
+}
+
+void cholesky_upper(cudaStream_t s, int k, double* G, int64_t ld, int* status) {
+  cholesky_upper_kernel<<<1, 1024, 0, s>>>(k, G, ld, status);
+  CK_LAUNCH();
+  ++g_kernel_launches;
+}
+
+void invert_upper(cudaStream_t s, int k, const double* R, int64_t ld, double* Rinv) {
+  invert_upper_kernel<<<(k + 63) / 64, 64, 0, s>>>(k, R, ld, Rinv);
+  CK_LAUNCH();
+  ++g_kernel_launches;
+}
+
+}  // namespace dav

@@ -1,0 +1,580 @@
+// Device-resident block Davidson driver.
+//
+// What the reference does per iteration (davidson.f90:138-229) and what happens here instead:
+//   reference                                        | here (same subspaces, same Ritz pairs)
+//   -------------------------------------------------+---------------------------------------------------
+//   A*V recomputed for the whole basis (:223)        | AV, BV kept in HBM; only the new block is multiplied
+//   k DGEMVs for the residuals (:163-170)            | R = AV*Y - (BV|V)*Y*diag(theta) from the stored products
+//   Householder QR of all of [V, C] (:213)           | V kept; C projected against V twice and orthonormalised
+//                                                    | by SVQB (Gram matrix -> Jacobi -> C * U * S^-1/2)
+//   full re-projection V^T (A V) (:223)              | only the new block columns [V Q]^T (A Q) are computed
+//   DSYEV / DSYGV (:153,155)                         | one-CTA Jacobi (+ Bp^-1/2 congruence for DSYGV)
+//   collapse V <- V*y(:, :2L) (:218)                 | same, applied to V, AV, BV (no matvec); the B-orthonormal
+//                                                    | collapsed basis is re-orthonormalised (same span)
+// The basis schedule (2L, 4L, ... until k > max_dim, then back to 2L), the corrections for ALL k
+// Ritz pairs, the sticky (dense) / non-sticky (free) convergence tests and the outputs are the
+// reference's.  tests/device_model.py restates this flow in numpy and is checked against the oracle.
+//
+// Multi-GPU: rows of A, B, V, AV, BV, R, C are block-partitioned over the ranks.  Per iteration the
+// ranks exchange only the new basis block (all-gather, n x b), the small projection / Gram
+// partials (all-reduce, <= 2k x k) and the residual norms (all-reduce, k scalars).
+#include "solver.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+using namespace dav;
+
+namespace {
+enum { SPAN_MATVEC = 0, SPAN_RR = 1, SPAN_ORTH = 2, SPAN_RESID = 3, SPAN_PROJ = 4, SPAN_INIT = 5, SPAN_TOTAL = 6 };
+constexpr int EV_POOL = 1024;
+}  // namespace
+
+dav_solver::dav_solver(int device_, int rank, int world, const void* id128) : device(device_) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    (void)cudaGetLastError();
+    DAV_THROW(DAV_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+              e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= count) DAV_THROW(DAV_ERR_INVALID, "device %d out of range (%d devices)", device, count);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    DAV_THROW(DAV_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+              prop.minor);
+  comm.init(rank, world, id128);
+  CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  std::memset(&stats, 0, sizeof(stats));
+}
+
+dav_solver::~dav_solver() {
+  cudaSetDevice(device);
+  for (int w = 0; w < 2; ++w)
+    if (mat[w].plan) matvec_plan_destroy(mat[w].plan);
+  for (cudaEvent_t ev : ev_pool) cudaEventDestroy(ev);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+void dav_solver::set_dims(int64_t n_) {
+  if (n_ <= 0) DAV_THROW(DAV_ERR_INVALID, "matrix dimension must be positive");
+  for (int w = 0; w < 2; ++w)
+    if (mat[w].kind != NONE && mat[w].n != n_)
+      DAV_THROW(DAV_ERR_STATE, "matrix and second_matrix must have the same dimension (%lld vs %lld)",
+                (long long)mat[w].n, (long long)n_);
+  n = n_;
+  int64_t r0, r1;
+  dav_partition_rows(n, comm.world(), comm.rank(), &r0, &r1);
+  row0 = r0;
+  nl = r1 - r0;
+  chunk = comm.world() > 1 ? round_up(ceil_div(n, comm.world()), 128) : n;
+}
+
+void dav_solver::clear_matrix(int which) {
+  Matrix& m = mat[which];
+  if (m.plan) matvec_plan_destroy(m.plan);
+  m.plan = nullptr;
+  m.A.release();
+  m.diag.release();
+  m.diag_valid = false;
+  m.kind = NONE;
+  m.n = 0;
+}
+
+void dav_solver::generate_diagonal_dominant(int which, int64_t n_, double sparsity, int has_diag, double diag_val,
+                                            uint64_t seed) {
+  CK(cudaSetDevice(device));
+  clear_matrix(which);
+  set_dims(n_);
+  Matrix& m = mat[which];
+  m.lda = round_up(std::max<int64_t>(nl, 1), 16);
+  m.A.alloc((size_t)m.lda * n);
+  gen_diag_dominant(stream, m.A.p, m.lda, nl, n, row0, sparsity, has_diag, diag_val, seed);
+  CK(cudaStreamSynchronize(stream));
+  m.kind = DENSE;
+  m.n = n;
+}
+
+void dav_solver::upload(int which, int64_t n_, const double* host, int64_t ld) {
+  CK(cudaSetDevice(device));
+  if (!host || ld < n_) DAV_THROW(DAV_ERR_INVALID, "upload: bad host matrix / leading dimension");
+  clear_matrix(which);
+  set_dims(n_);
+  Matrix& m = mat[which];
+  m.lda = round_up(std::max<int64_t>(nl, 1), 16);
+  m.A.alloc((size_t)m.lda * n);
+  if (nl > 0)
+    CK(cudaMemcpy2DAsync(m.A.p, (size_t)m.lda * 8, host + row0, (size_t)ld * 8, (size_t)nl * 8, (size_t)n,
+                         cudaMemcpyHostToDevice, stream));
+  CK(cudaStreamSynchronize(stream));
+  m.kind = DENSE;
+  m.n = n;
+}
+
+void dav_solver::set_operator(int which, int64_t n_, int op) {
+  CK(cudaSetDevice(device));
+  if (op < DAV_OP_BENCHMARK_MTX || op > DAV_OP_TEST_STX) DAV_THROW(DAV_ERR_INVALID, "unknown built-in operator %d", op);
+  clear_matrix(which);
+  set_dims(n_);
+  mat[which].kind = BUILTIN;
+  mat[which].op = op;
+  mat[which].n = n;
+}
+
+void dav_solver::set_callback(int which, int64_t n_, dav_gemv_fn fn, void* ctx, const double* diag) {
+  CK(cudaSetDevice(device));
+  if (!fn) DAV_THROW(DAV_ERR_INVALID, "null operator callback");
+  if (comm.world() > 1) DAV_THROW(DAV_ERR_INVALID, "host callbacks are supported on one rank only");
+  clear_matrix(which);
+  set_dims(n_);
+  Matrix& m = mat[which];
+  m.kind = CALLBACK;
+  m.fn = fn;
+  m.ctx = ctx;
+  m.n = n;
+  if (diag) {
+    m.diag.alloc((size_t)std::max<int64_t>(nl, 1));
+    CK(cudaMemcpy(m.diag.p, diag + row0, (size_t)nl * 8, cudaMemcpyHostToDevice));
+    m.diag_valid = true;
+  }
+}
+
+void dav_solver::download(int which, double* host_rows, int64_t ld) {
+  CK(cudaSetDevice(device));
+  Matrix& m = mat[which];
+  if (m.kind != DENSE) DAV_THROW(DAV_ERR_STATE, "download: no dense matrix in slot %d", which);
+  if (nl > 0)
+    CK(cudaMemcpy2D(host_rows, (size_t)ld * 8, m.A.p, (size_t)m.lda * 8, (size_t)nl * 8, (size_t)n,
+                    cudaMemcpyDeviceToHost));
+}
+
+void dav_solver::ensure_etab() {
+  if (etab.n == (size_t)n && etab.p) return;
+  // e_t = dble(exp(real(t)/real(dim))) in SINGLE precision (benchmark_free.f90:50,53) -- built with the
+  // host's expf so the table carries exactly the bits the oracle (and gfortran) see.
+  std::vector<double> h((size_t)n);
+  const float fn = (float)n;
+  for (int64_t t = 0; t < n; ++t) h[(size_t)t] = (double)expf((float)(t + 1) / fn);
+  etab.release();
+  etab.alloc((size_t)n);
+  CK(cudaMemcpy(etab.p, h.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+}
+
+void dav_solver::ensure_diag(int which) {
+  Matrix& m = mat[which];
+  if (m.diag_valid) return;
+  m.diag.alloc((size_t)std::max<int64_t>(nl, 1));
+  if (m.kind == DENSE) {
+    extract_diag(stream, m.A.p, m.lda, nl, row0, m.diag.p);
+  } else if (m.kind == BUILTIN) {
+    ensure_etab();
+    free_diag_builtin(stream, m.op, n, row0, nl, etab.p, m.diag.p);
+  } else if (m.kind == CALLBACK) {
+    // extract_diagonal_free (davidson.f90:490-523): apply the operator to unit vectors, 64 at a time
+    const int blk = 64;
+    std::vector<double> x((size_t)n * blk), y((size_t)n * blk), d((size_t)n);
+    for (int64_t c0 = 0; c0 < n; c0 += blk) {
+      const int w = (int)std::min<int64_t>(blk, n - c0);
+      std::fill(x.begin(), x.begin() + (size_t)n * w, 0.0);
+      for (int j = 0; j < w; ++j) x[(size_t)j * n + c0 + j] = 1.0;
+      m.fn(x.data(), y.data(), n, w, m.ctx);
+      for (int j = 0; j < w; ++j) d[(size_t)(c0 + j)] = y[(size_t)j * n + c0 + j];
+    }
+    CK(cudaMemcpyAsync(m.diag.p, d.data() + row0, (size_t)nl * 8, cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+  }
+  m.diag_valid = true;
+}
+
+void dav_solver::ensure_plan(int which, int max_b) {
+  Matrix& m = mat[which];
+  if (m.kind != DENSE || m.plan) return;
+  if (matvec_impl == DAV_MATVEC_SIMT) return;
+  if (!matvec_dmma_supported()) {
+    if (matvec_impl == DAV_MATVEC_TMA_DMMA) DAV_THROW(DAV_ERR_CUDA, "TMA tensor maps unavailable from this driver");
+    return;
+  }
+  m.plan = matvec_plan_create(m.A.p, nl, n, m.lda, max_b);
+}
+
+int dav_solver::begin_span(int kind) {
+  if (ev_used + 2 > (int)ev_pool.size()) {
+    if ((int)ev_pool.size() >= EV_POOL) return -1;
+    for (int i = 0; i < 64; ++i) {
+      cudaEvent_t ev;
+      CK(cudaEventCreate(&ev));
+      ev_pool.push_back(ev);
+    }
+  }
+  const int a = ev_used++, b = ev_used++;
+  CK(cudaEventRecord(ev_pool[a], stream));
+  spans.push_back(Span{a, b, kind});
+  return (int)spans.size() - 1;
+}
+
+void dav_solver::end_span(int id) {
+  if (id < 0) return;
+  CK(cudaEventRecord(ev_pool[spans[id].b], stream));
+}
+
+const double* dav_solver::gather_rows(const double* Xlocal, int64_t ldx, int b, int64_t* ld_out) {
+  if (!comm.active()) {
+    *ld_out = ldx;
+    return Xlocal;
+  }
+  stage_s.alloc((size_t)chunk * b);
+  stage_r.alloc((size_t)chunk * b * comm.world());
+  Xfull.alloc((size_t)n * b);
+  stage_block(stream, Xlocal, ldx, nl, chunk, b, stage_s.p);
+  comm.allgather(stage_s.p, stage_r.p, (size_t)chunk * b * 8, stream);
+  unstage_allgather(stream, stage_r.p, comm.world(), chunk, n, b, Xfull.p, n);
+  *ld_out = n;
+  return Xfull.p;
+}
+
+void dav_solver::apply(int which, const double* Xlocal, int64_t ldx, int b, double* W, int64_t ldw) {
+  int64_t ldf = 0;
+  const double* Xf = gather_rows(Xlocal, ldx, b, &ldf);
+  apply_full(which, Xf, ldf, b, W, ldw);
+}
+
+void dav_solver::apply_full(int which, const double* Xf, int64_t ldx, int b, double* W, int64_t ldw) {
+  Matrix& m = mat[which];
+  const int sp = begin_span(SPAN_MATVEC);
+  if (m.kind == DENSE) {
+    ensure_plan(which, b);
+    if (m.plan && matvec_impl != DAV_MATVEC_SIMT)
+      matvec_dmma(stream, m.plan, b, Xf, ldx, W, ldw);
+    else
+      gemm(stream, false, nl, b, n, 1.0, m.A.p, m.lda, Xf, ldx, 0.0, W, ldw, nullptr, 0);
+  } else if (m.kind == BUILTIN) {
+    ensure_etab();
+    free_matmul_builtin(stream, m.op, n, row0, nl, b, etab.p, Xf, ldx, W, ldw);
+  } else if (m.kind == CALLBACK) {
+    host_x.resize((size_t)n * b);
+    host_y.resize((size_t)n * b);
+    CK(cudaMemcpy2DAsync(host_x.data(), (size_t)n * 8, Xf, (size_t)ldx * 8, (size_t)n * 8, (size_t)b,
+                         cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    m.fn(host_x.data(), host_y.data(), n, b, m.ctx);
+    CK(cudaMemcpy2DAsync(W, (size_t)ldw * 8, host_y.data() + row0, (size_t)n * 8, (size_t)nl * 8, (size_t)b,
+                         cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+  } else {
+    DAV_THROW(DAV_ERR_STATE, "no matrix set in slot %d", which);
+  }
+  end_span(sp);
+  stats.matvec_launches += 1;
+  stats.matvec_bytes += 8.0 * (double)nl * (double)n + 8.0 * (double)n * b + 8.0 * (double)nl * b;
+  stats.matvec_flops += 2.0 * (double)nl * (double)n * b;
+  stats.last_matvec_b = b;
+}
+
+void dav_solver::alloc_work(int lowest, int kcap_) {
+  kcap = kcap_;
+  ldv = round_up(std::max<int64_t>(nl, 1), 16);
+  const size_t nk = (size_t)ldv * kcap;
+  V.alloc(nk); AV.alloc(nk); R.alloc(nk); C.alloc(nk); T.alloc(nk);
+  if (mat[1].kind != NONE) BV.alloc(nk);
+  const size_t kk = (size_t)kcap * kcap;
+  Ap.alloc(kk); Bp.alloc(kk); Y.alloc(kk); G.alloc(kk); U.alloc(kk); Tm.alloc(kk); S1.alloc(kk); S2.alloc(kk);
+  Z.alloc(kk);
+  theta.alloc(kcap); sv.alloc(kcap); D.alloc(kcap); norms2.alloc(kcap);
+  jscratch.alloc(2 * (size_t)(kcap + 2) * (kcap + 2));
+  partial.alloc((size_t)kcap * 64);
+  gemm_ws.alloc(std::max<size_t>(kk * 64, (size_t)1 << 22));
+  small.alloc(16);
+  status.alloc(4);
+  flags.alloc(kcap);
+  idx.alloc(2 * (size_t)lowest);
+  cand_val.alloc((size_t)2 * lowest * std::max(1, comm.world()) + 2 * (size_t)lowest);
+  cand_idx.alloc((size_t)2 * lowest * std::max(1, comm.world()) + 2 * (size_t)lowest);
+  // everything the loop touches is allocated up front: no cudaMalloc inside the iteration
+  const int bmax = std::max(2 * lowest, kcap / 2);
+  const bool any_free = mat[0].kind != DENSE || (mat[1].kind != NONE && mat[1].kind != DENSE);
+  if (comm.active() || any_free) Xfull.alloc((size_t)n * bmax);
+  if (comm.active()) {
+    stage_s.alloc((size_t)chunk * bmax);
+    stage_r.alloc((size_t)chunk * bmax * comm.world());
+  }
+  for (int w = 0; w < 2; ++w) ensure_plan(w, bmax);
+}
+
+void dav_solver::check_status(const char* where) {
+  int h = 0;
+  CK(cudaMemcpyAsync(&h, status.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  if (h & 2)
+    DAV_THROW(DAV_ERR_NOT_POSDEF, "%s: projected second_matrix / Gram matrix is not positive definite", where);
+  if (h & 1) DAV_THROW(DAV_ERR_NO_CONVERGENCE, "%s: Jacobi eigensolver failed (NaN input or no convergence)", where);
+}
+
+// Rayleigh-Ritz on the k x k projections (davidson.f90:152-156; lapack_wrapper.f90:14-91).
+// Generalized: Bp = U S U^T, Tm = U S^-1/2, (Tm^T Ap Tm) Z = Z theta, Y = Tm Z  => Y^T Bp Y = I like DSYGV itype=1.
+void dav_solver::rayleigh_ritz(int k, bool gev) {
+  const int sp = begin_span(SPAN_RR);
+  copy_matrix(stream, k, k, Ap.p, kcap, S1.p, k);
+  if (!gev) {
+    jacobi_eigh(stream, k, S1.p, Y.p, theta.p, jscratch.p, status.p);
+  } else {
+    copy_matrix(stream, k, k, Bp.p, kcap, S2.p, k);
+    jacobi_eigh(stream, k, S2.p, U.p, sv.p, jscratch.p, status.p);
+    scale_cols_rsqrt_checked(stream, k, U.p, sv.p, Tm.p, status.p);
+    symmetrize_from_upper(stream, k, S1.p, k);
+    gemm(stream, false, k, k, k, 1.0, S1.p, k, Tm.p, k, 0.0, Z.p, k, nullptr, 0);
+    gemm(stream, true, k, k, k, 1.0, Tm.p, k, Z.p, k, 0.0, S1.p, k, nullptr, 0);
+    jacobi_eigh(stream, k, S1.p, Z.p, theta.p, jscratch.p, status.p);
+    gemm(stream, false, k, k, k, 1.0, Tm.p, k, Z.p, k, 0.0, Y.p, k, nullptr, 0);
+  }
+  end_span(sp);
+}
+
+// P(0:k, 0:k) = V^T W for the whole basis (initial step and after a collapse; davidson.f90:131,223)
+void dav_solver::full_projection(int which, int k) {
+  const int sp = begin_span(SPAN_PROJ);
+  double* W = which ? BV.p : AV.p;
+  double* P = which ? Bp.p : Ap.p;
+  gemm(stream, true, k, k, nl, 1.0, V.p, ldv, W, ldv, 0.0, G.p, k, gemm_ws.p, gemm_ws.n);
+  allreduce(G.p, (size_t)k * k);
+  copy_matrix(stream, k, k, G.p, k, P, kcap);
+  end_span(sp);
+}
+
+// P(0:kold+b, kold:kold+b) = [V Q]^T (W Q), mirrored to the lower triangle (incremental form of :223)
+void dav_solver::project_new_block(int which, int kold, int b) {
+  const int sp = begin_span(SPAN_PROJ);
+  double* W = (which ? BV.p : AV.p) + (size_t)kold * ldv;
+  double* P = which ? Bp.p : Ap.p;
+  const int kn = kold + b;
+  gemm(stream, true, kn, b, nl, 1.0, V.p, ldv, W, ldv, 0.0, G.p, kn, gemm_ws.p, gemm_ws.n);
+  allreduce(G.p, (size_t)kn * b);
+  copy_matrix(stream, kn, b, G.p, kn, P + (size_t)kold * kcap, kcap);
+  symmetrize_from_upper(stream, kn, P, kcap);
+  end_span(sp);
+}
+
+// Replaces lapack_qr on [V, C] (davidson.f90:210-213): V is already orthonormal, so only the new block is
+// touched: normalise columns, then repeat { C -= V (V^T C);  G = C^T C;  C <- C * (D U S^-1/2) } (SVQB)
+// until a pass starts from an already orthonormal block.  Rank-deficient directions (S below threshold)
+// are refilled with pseudo-random vectors, which is what Householder QR effectively returns for them.
+void dav_solver::orthonormalize_block(double* Cblk, int b, int kold, double* dest) {
+  const int sp = begin_span(SPAN_ORTH);
+  double* cur = Cblk;
+  double* other = T.p;
+  col_norms2(stream, nl, b, cur, ldv, partial.p, norms2.p);
+  allreduce(norms2.p, b);
+  scale_cols_rsqrt(stream, nl, b, cur, ldv, norms2.p);
+  bool done = false;
+  for (int pass = 0; pass < 8 && !done; ++pass) {
+    gemm(stream, true, kold, b, nl, 1.0, V.p, ldv, cur, ldv, 0.0, G.p, kold, gemm_ws.p, gemm_ws.n);
+    allreduce(G.p, (size_t)kold * b);
+    gemm(stream, false, nl, b, kold, -1.0, V.p, ldv, G.p, kold, 1.0, cur, ldv, nullptr, 0);
+    gemm(stream, true, b, b, nl, 1.0, cur, ldv, cur, ldv, 0.0, S1.p, b, gemm_ws.p, gemm_ws.n);
+    allreduce(S1.p, (size_t)b * b);
+    if (pass >= 1) {
+      max_abs_dev(stream, kold, b, G.p, kold, false, small.p);
+      max_abs_dev(stream, b, b, S1.p, b, true, small.p + 1);
+      double h[2];
+      CK(cudaMemcpyAsync(h, small.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      // this pass starts from a block that is orthonormal to 1e-6: after it the error is O(eps)
+      if (h[0] < 1e-6 && h[1] < 1e-6) done = true;
+    }
+    gram_prescale(stream, b, S1.p, D.p);
+    jacobi_eigh(stream, b, S1.p, U.p, sv.p, jscratch.p, status.p);
+    svqb_make_T(stream, b, U.p, sv.p, D.p, Tm.p, flags.p);
+    gemm(stream, false, nl, b, b, 1.0, cur, ldv, Tm.p, b, 0.0, other, ldv, nullptr, 0);
+    fill_random_cols(stream, other, ldv, nl, row0, flags.p, b, 0x5EEDULL + (uint64_t)pass);
+    std::swap(cur, other);
+  }
+  if (!done) DAV_THROW(DAV_ERR_NO_CONVERGENCE, "block orthonormalisation did not converge");
+  if (cur != dest) copy_matrix(stream, nl, b, cur, ldv, dest, ldv);
+  end_span(sp);
+}
+
+void dav_solver::gjd_correction(int k, bool gev) {
+  (void)k; (void)gev;
+  DAV_THROW(DAV_ERR_INVALID, "GJD correction is not available in this build");
+}
+
+int dav_solver::solve(int lowest, int method, int max_iterations, double tolerance, int max_dim_sub,
+                      double* eigenvalues, double* eigenvectors, int64_t ldvec, int* iters) {
+  CK(cudaSetDevice(device));
+  if (mat[0].kind == NONE) DAV_THROW(DAV_ERR_STATE, "dav_solve: no matrix set");
+  if (lowest < 1) DAV_THROW(DAV_ERR_INVALID, "lowest must be >= 1");
+  if (method != DAV_METHOD_DPR && method != DAV_METHOD_GJD) DAV_THROW(DAV_ERR_INVALID, "unknown method %d", method);
+  if (max_iterations < 1) DAV_THROW(DAV_ERR_INVALID, "max_iterations must be >= 1");
+  const bool free_mode = mat[0].kind != DENSE;
+  const bool gev = mat[1].kind != NONE;
+  if (free_mode && !gev)
+    DAV_THROW(DAV_ERR_STATE, "the matrix-free path needs both operators (fun_second_matrix_gemv is not optional)");
+  if (free_mode) method = DAV_METHOD_DPR;  // davidson.f90:428: `method` is ignored, always DPR
+  const int L = lowest, k0 = 2 * L;                                  // davidson.f90:108
+  const int max_dim = max_dim_sub > 0 ? max_dim_sub : 10 * L;        // davidson.f90:115-119
+  if ((int64_t)k0 > n) DAV_THROW(DAV_ERR_INVALID, "2*lowest = %d exceeds the matrix dimension %lld", k0, (long long)n);
+  if (eigenvectors && ldvec < n) DAV_THROW(DAV_ERR_INVALID, "eigenvector leading dimension too small");
+  int kc = std::max(k0, 2 * max_dim);
+  if ((int64_t)kc > n) kc = (int)std::max<int64_t>(k0, n);
+  alloc_work(L, kc);
+
+  std::memset(&stats, 0, sizeof(stats));
+  spans.clear();
+  ev_used = 0;
+  const long long launches0 = g_kernel_launches;
+  CK(cudaMemsetAsync(status.p, 0, 4 * sizeof(int), stream));
+  const int sp_total = begin_span(SPAN_TOTAL);
+
+  // ---- 1. initial basis: unit vectors at the 2L smallest diagonal entries (davidson.f90:127-128)
+  int sp = begin_span(SPAN_INIT);
+  ensure_diag(0);
+  if (gev) ensure_diag(1);
+  topk_smallest(stream, mat[0].diag.p, nullptr, nl, row0, k0, cand_val.p, cand_idx.p, status.p);
+  if (comm.active()) {
+    const int P = comm.world();
+    double* allv = cand_val.p + k0;
+    int64_t* alli = cand_idx.p + k0;
+    comm.allgather(cand_val.p, allv, (size_t)k0 * 8, stream);
+    comm.allgather(cand_idx.p, alli, (size_t)k0 * 8, stream);
+    topk_smallest(stream, allv, alli, (int64_t)k0 * P, 0, k0, cand_val.p, idx.p, status.p);
+  } else {
+    CK(cudaMemcpyAsync(idx.p, cand_idx.p, (size_t)k0 * 8, cudaMemcpyDeviceToDevice, stream));
+  }
+  int k = k0;
+  fill_zero(stream, V.p, (size_t)ldv * k);
+  set_onehot(stream, V.p, ldv, nl, row0, idx.p, k);
+  end_span(sp);
+  for (int w = 0; w < (gev ? 2 : 1); ++w) {
+    double* W = w ? BV.p : AV.p;
+    if (mat[w].kind == DENSE) {
+      sp = begin_span(SPAN_INIT);
+      gather_columns(stream, mat[w].A.p, mat[w].lda, nl, idx.p, k, W, ldv);  // A*V for one-hot V
+      end_span(sp);
+    } else {
+      Xfull.alloc((size_t)n * k);
+      fill_zero(stream, Xfull.p, (size_t)n * k);
+      set_onehot(stream, Xfull.p, n, n, 0, idx.p, k);
+      apply_full(w, Xfull.p, n, k, W, ldv);
+    }
+    full_projection(w, k);  // davidson.f90:131,134
+  }
+
+  // ---- outer loop (davidson.f90:138)
+  std::vector<char> has_converged(L, 0);
+  std::vector<double> errs(L), hn2(L);
+  bool converged = false;
+  int it = 0;
+  for (it = 1; it <= max_iterations; ++it) {
+    rayleigh_ritz(k, gev);                                            // step 3
+    sp = begin_span(SPAN_RESID);
+    // step 4.1 from the stored products: R = AV*Y - (BV|V)*Y*diag(theta), all k columns
+    gemm(stream, false, nl, k, k, 1.0, AV.p, ldv, Y.p, k, 0.0, R.p, ldv, nullptr, 0);
+    gemm(stream, false, nl, k, k, 1.0, gev ? BV.p : V.p, ldv, Y.p, k, 0.0, C.p, ldv, nullptr, 0);
+    residual_dpr(stream, nl, k, R.p, ldv, C.p, ldv, theta.p, mat[0].diag.p, gev ? mat[1].diag.p : nullptr,
+                 method == DAV_METHOD_DPR, partial.p, norms2.p);
+    allreduce(norms2.p, k);
+    end_span(sp);
+    CK(cudaMemcpyAsync(hn2.data(), norms2.p, (size_t)L * 8, cudaMemcpyDeviceToHost, stream));
+    check_status("Rayleigh-Ritz");  // synchronises the stream
+    // step 4.2 (davidson.f90:173-178; free :412-416)
+    double max_err = 0.0;
+    bool all_now = true;
+    for (int j = 0; j < L; ++j) {
+      errs[j] = std::sqrt(hn2[j]);
+      max_err = std::max(max_err, errs[j]);
+      if (errs[j] < tolerance) has_converged[j] = 1;
+      else all_now = false;
+    }
+    if (stats.trace_len < 64) {
+      stats.trace_k[stats.trace_len] = k;
+      stats.trace_err[stats.trace_len] = max_err;
+      stats.trace_len++;
+    }
+    stats.iterations = it;
+    if (free_mode) converged = all_now;                               // non-sticky (:416)
+    else converged = std::all_of(has_converged.begin(), has_converged.end(), [](char c) { return c != 0; });
+    if (converged || it == max_iterations) {
+      // eigenvalues = theta(1:L), eigenvectors = V*Y(:, 1:L) of this Rayleigh-Ritz step (:186-187)
+      gemm(stream, false, nl, L, k, 1.0, V.p, ldv, Y.p, k, 0.0, T.p, ldv, nullptr, 0);
+      CK(cudaMemcpyAsync(eigenvalues, theta.p, (size_t)L * 8, cudaMemcpyDeviceToHost, stream));
+      if (eigenvectors) {
+        int64_t ldf = 0;
+        const double* Xf = gather_rows(T.p, ldv, L, &ldf);
+        const int64_t rows = comm.active() ? n : nl;
+        CK(cudaMemcpy2DAsync(eigenvectors, (size_t)ldvec * 8, Xf, (size_t)ldf * 8, (size_t)rows * 8, (size_t)L,
+                             cudaMemcpyDeviceToHost, stream));
+      }
+      CK(cudaStreamSynchronize(stream));
+      if (converged) break;
+    }
+    if (it == max_iterations) { it = max_iterations + 1; break; }
+
+    if (k <= max_dim) {                                               // step 5 (:195)
+      if ((int64_t)2 * k > n || 2 * k > kcap)
+        DAV_THROW(DAV_ERR_BASIS_TOO_LARGE, "basis of %d columns cannot be expanded inside an n = %lld problem", k,
+                  (long long)n);
+      if (method == DAV_METHOD_GJD) gjd_correction(k, gev);           // C <- GJD corrections
+      double* Q = V.p + (size_t)k * ldv;
+      orthonormalize_block(C.p, k, k, Q);                             // steps 6-7 (:210-213)
+      for (int w = 0; w < (gev ? 2 : 1); ++w) {
+        double* W = (w ? BV.p : AV.p) + (size_t)k * ldv;
+        apply(w, Q, ldv, k, W, ldv);                                  // the block matvec
+        project_new_block(w, k, k);
+      }
+      k *= 2;
+    } else {                                                          // collapse (:218)
+      sp = begin_span(SPAN_ORTH);
+      double* bufs[3] = {V.p, AV.p, gev ? BV.p : nullptr};
+      for (double* Bf : bufs) {
+        if (!Bf) continue;
+        gemm(stream, false, nl, k0, k, 1.0, Bf, ldv, Y.p, k, 0.0, T.p, ldv, nullptr, 0);
+        copy_matrix(stream, nl, k0, T.p, ldv, Bf, ldv);
+      }
+      if (gev) {
+        // the collapsed basis is B-orthonormal, not 2-orthonormal: restore V^T V = I (same span)
+        gemm(stream, true, k0, k0, nl, 1.0, V.p, ldv, V.p, ldv, 0.0, S1.p, k0, gemm_ws.p, gemm_ws.n);
+        allreduce(S1.p, (size_t)k0 * k0);
+        jacobi_eigh(stream, k0, S1.p, U.p, sv.p, jscratch.p, status.p);
+        scale_cols_rsqrt_checked(stream, k0, U.p, sv.p, Tm.p, status.p);
+        for (double* Bf : bufs) {
+          gemm(stream, false, nl, k0, k0, 1.0, Bf, ldv, Tm.p, k0, 0.0, T.p, ldv, nullptr, 0);
+          copy_matrix(stream, nl, k0, T.p, ldv, Bf, ldv);
+        }
+      }
+      end_span(sp);
+      k = k0;
+      full_projection(0, k);
+      if (gev) full_projection(1, k);
+    }
+  }
+  end_span(sp_total);
+  CK(cudaStreamSynchronize(stream));
+
+  // ---- statistics
+  for (const Span& s : spans) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev_pool[s.a], ev_pool[s.b]) != cudaSuccess) { (void)cudaGetLastError(); continue; }
+    switch (s.kind) {
+      case SPAN_MATVEC: stats.matvec_ms += ms; stats.last_matvec_ms = ms; break;
+      case SPAN_RR: stats.rr_ms += ms; break;
+      case SPAN_ORTH: stats.orth_ms += ms; break;
+      case SPAN_RESID: stats.resid_ms += ms; break;
+      case SPAN_PROJ: stats.proj_ms += ms; break;
+      case SPAN_INIT: stats.init_ms += ms; break;
+      case SPAN_TOTAL: stats.solve_ms = ms; break;
+    }
+  }
+  stats.kernel_launches = (int)(g_kernel_launches - launches0);
+
+  if (converged) {
+    *iters = it;
+  } else if (!free_mode) {
+    *iters = max_iterations + 1;                                      // davidson.f90:232-235
+    if (comm.rank() == 0) std::printf(" Warning: Algorithm did not converge!!\n");
+  } else {
+    if (comm.rank() == 0) std::printf(" Warning: Algorithm did not converge!!\n");  // :444-446; iters untouched (:417)
+  }
+  return DAV_OK;
+}

@@ -1,0 +1,82 @@
+// Device-resident block Davidson driver (replaces generalized_eigensolver_dense / _free,
+// davidson.f90:51-246 and :277-460).  See solver.cu for the algorithm notes.
+#pragma once
+#include <vector>
+
+#include "comm.cuh"
+#include "kernels.cuh"
+
+struct dav_solver {
+  enum Kind { NONE = 0, DENSE = 1, BUILTIN = 2, CALLBACK = 3 };
+  struct Matrix {
+    Kind kind = NONE;
+    int64_t n = 0;
+    dav::DevBuf<double> A;  // DENSE: local row block, nl x n column-major, leading dimension lda
+    int64_t lda = 0;
+    dav::MatvecPlan* plan = nullptr;
+    int op = 0;                      // BUILTIN
+    dav_gemv_fn fn = nullptr;        // CALLBACK
+    void* ctx = nullptr;
+    dav::DevBuf<double> diag;        // local diagonal entries
+    bool diag_valid = false;
+  };
+
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  dav::Comm comm;
+  int64_t n = 0, nl = 0, row0 = 0, chunk = 0;  // global size, local rows, first local row, rows per rank
+  Matrix mat[2];
+  dav::DevBuf<double> etab;  // e_t table of the built-in operators
+  int matvec_impl = DAV_MATVEC_AUTO;
+  dav_stats_t stats;
+
+  // ---- work space of a solve
+  int64_t ldv = 0;
+  int kcap = 0;
+  dav::DevBuf<double> V, AV, BV, R, C, T, Xfull, stage_s, stage_r;
+  dav::DevBuf<double> Ap, Bp, Y, theta, G, U, sv, D, Tm, S1, S2, Z, jscratch, norms2, partial, gemm_ws, small;
+  dav::DevBuf<int> status, flags;
+  dav::DevBuf<int64_t> idx, cand_idx;
+  dav::DevBuf<double> cand_val;
+  std::vector<double> host_x, host_y;  // callback staging
+  std::vector<cudaEvent_t> ev_pool;
+  struct Span { int a, b, kind; };
+  std::vector<Span> spans;
+  int ev_used = 0;
+
+  dav_solver(int device, int rank, int world, const void* id128);
+  ~dav_solver();
+
+  void set_dims(int64_t n);
+  void clear_matrix(int which);
+  void generate_diagonal_dominant(int which, int64_t n, double sparsity, int has_diag, double diag_val,
+                                  uint64_t seed);
+  void upload(int which, int64_t n, const double* host, int64_t ld);
+  void set_operator(int which, int64_t n, int op);
+  void set_callback(int which, int64_t n, dav_gemv_fn fn, void* ctx, const double* diag);
+  void download(int which, double* host_rows, int64_t ld);
+  void ensure_etab();
+  void ensure_diag(int which);
+  void ensure_plan(int which, int max_b);
+
+  // W(local rows x b) = M_which * X, X given as the local row block (nl x b, ldx) of a row-sharded block
+  void apply(int which, const double* Xlocal, int64_t ldx, int b, double* W, int64_t ldw);
+  // same with X already complete (n x b) on this rank
+  void apply_full(int which, const double* Xfull_, int64_t ldx, int b, double* W, int64_t ldw);
+  const double* gather_rows(const double* Xlocal, int64_t ldx, int b, int64_t* ld_out);
+
+  int solve(int lowest, int method, int max_iterations, double tolerance, int max_dim_sub, double* eigenvalues,
+            double* eigenvectors, int64_t ldvec, int* iters);
+
+  // pieces of the iteration
+  void alloc_work(int lowest, int kcap_);
+  void rayleigh_ritz(int k, bool gev);
+  void orthonormalize_block(double* Cblk, int b, int kold, double* dest);
+  void gjd_correction(int k, bool gev);
+  void project_new_block(int which, int kold, int b);
+  void full_projection(int which, int k);
+  void allreduce(double* buf, size_t count) { comm.allreduce_sum(buf, count, stream); }
+  int begin_span(int kind);
+  void end_span(int id);
+  void check_status(const char* where);
+};

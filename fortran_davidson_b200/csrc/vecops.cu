@@ -1,0 +1,336 @@
+// n x k vector-block kernels, generators and layout helpers.  All HBM-bound streaming kernels:
+// coalesced along the row index (column-major blocks), grids sized in multiples of the SM count.
+#include <algorithm>
+
+#include "kernels.cuh"
+
+namespace dav {
+namespace {
+
+constexpr int SMS = 148;
+
+__global__ void fill_zero_kernel(double* p, size_t count) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (size_t)gridDim.x * blockDim.x)
+    p[e] = 0.0;
+}
+
+__global__ void copy_matrix_kernel(int64_t rows, int64_t cols, const double* __restrict__ src, int64_t lds,
+                                   double* __restrict__ dst, int64_t ldd) {
+  const int64_t total = rows * cols;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e % rows, j = e / rows;
+    dst[i + j * ldd] = src[i + j * lds];
+  }
+}
+
+// generate_diagonal_dominant (array_utils.f90:86-113) for the local row block [row0, row0+nl)
+__global__ void gen_diag_dominant_kernel(double* __restrict__ A, int64_t lda, int64_t nl, int64_t n, int64_t row0,
+                                         double sparsity, int has_diag, double diag_val, uint64_t seed) {
+  // grid.y walks columns, x walks rows: coalesced stores along the column
+  for (int64_t j = blockIdx.y; j < n; j += gridDim.y) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nl; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t gi = row0 + i;
+      double v;
+      if (gi == j) v = has_diag ? diag_val : (double)(gi + 1);
+      else {
+        const uint64_t lo = (uint64_t)(gi < j ? gi : j), hi = (uint64_t)(gi < j ? j : gi);
+        v = uniform01(seed, lo, hi) * sparsity;
+      }
+      A[i + j * lda] = v;
+    }
+  }
+}
+
+__global__ void extract_diag_kernel(const double* __restrict__ A, int64_t lda, int64_t nl, int64_t row0,
+                                    double* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nl; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = A[i + (row0 + i) * lda];
+}
+
+// k smallest (value, global index) pairs in ascending lexicographic order: pass t finds the
+// smallest pair strictly greater than the pair picked by pass t-1.  One CTA.
+__global__ void __launch_bounds__(1024) topk_smallest_kernel(const double* __restrict__ diag,
+                                                             const int64_t* __restrict__ gidx, int64_t count,
+                                                             int64_t row0, int k, double* out_val, int64_t* out_idx,
+                                                             int* status) {
+  __shared__ double sval[32];
+  __shared__ long long sidx[32];
+  __shared__ double last_val;
+  __shared__ long long last_idx;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (threadIdx.x == 0) { last_val = -INFINITY; last_idx = -1; }
+  __syncthreads();
+  for (int t = 0; t < k; ++t) {
+    const double lv = last_val;
+    const long long li = last_idx;
+    double bv = INFINITY;
+    long long bi = 0x7fffffffffffffffLL;
+    for (int64_t e = threadIdx.x; e < count; e += blockDim.x) {
+      const double v = diag[e];
+      const long long g = gidx ? (long long)gidx[e] : (long long)(row0 + e);
+      if (!(v == v)) atomicOr(status, 1);
+      const bool after = (v > lv) || (v == lv && g > li);
+      const bool better = (v < bv) || (v == bv && g < bi);
+      if (after && better) { bv = v; bi = g; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { sval[wid] = bv; sidx[wid] = bi; }
+    __syncthreads();
+    if (wid == 0) {
+      bv = lane < nw ? sval[lane] : INFINITY;
+      bi = lane < nw ? sidx[lane] : 0x7fffffffffffffffLL;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) {
+        out_val[t] = bv;
+        out_idx[t] = (bi == 0x7fffffffffffffffLL) ? -1 : bi;
+        last_val = bv;
+        last_idx = bi;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void set_onehot_kernel(double* V, int64_t ldv, int64_t nl, int64_t row0, const int64_t* idx, int k) {
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const int64_t r = idx[j] - row0;
+    if (r >= 0 && r < nl) V[r + (int64_t)j * ldv] = 1.0;
+  }
+}
+
+__global__ void gather_columns_kernel(const double* __restrict__ A, int64_t lda, int64_t nl,
+                                      const int64_t* __restrict__ idx, int k, double* __restrict__ out, int64_t ldo) {
+  for (int j = blockIdx.y; j < k; j += gridDim.y) {
+    const double* src = A + idx[j] * lda;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nl; i += (int64_t)gridDim.x * blockDim.x)
+      out[i + (int64_t)j * ldo] = src[i];
+  }
+}
+
+constexpr int NCHUNK = 64;  // row chunks of the two-stage column reductions
+
+// partial[j * NCHUNK + c] = sum over chunk c of X(i,j)^2
+__global__ void col_norms2_stage1(int64_t nl, const double* __restrict__ X, int64_t ldx, double* __restrict__ partial) {
+  __shared__ double red[32];
+  const int j = blockIdx.y, c = blockIdx.x;
+  const int64_t per = (nl + NCHUNK - 1) / NCHUNK;
+  const int64_t beg = (int64_t)c * per, end = min(nl, beg + per);
+  double s = 0.0;
+  for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
+    const double v = X[i + (int64_t)j * ldx];
+    s = fma(v, v, s);
+  }
+  s = warp_sum(s);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) red[wid] = s;
+  __syncthreads();
+  if (wid == 0) {
+    double x = lane < (blockDim.x >> 5) ? red[lane] : 0.0;
+    x = warp_sum(x);
+    if (lane == 0) partial[(size_t)j * NCHUNK + c] = x;
+  }
+}
+
+__global__ void col_reduce_stage2(int k, const double* __restrict__ partial, double* __restrict__ out) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < k; j += gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int c = 0; c < NCHUNK; ++c) s += partial[(size_t)j * NCHUNK + c];
+    out[j] = s;
+  }
+}
+
+__global__ void scale_cols_rsqrt_kernel(int64_t nl, int k, double* __restrict__ X, int64_t ldx,
+                                        const double* __restrict__ n2) {
+  for (int j = blockIdx.y; j < k; j += gridDim.y) {
+    const double d = n2[j];
+    if (!(d > 0.0)) continue;
+    const double f = 1.0 / sqrt(d);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nl; i += (int64_t)gridDim.x * blockDim.x)
+      X[i + (int64_t)j * ldx] *= f;
+  }
+}
+
+// fused residual + norm partial + DPR: grid (NCHUNK, k)
+__global__ void residual_dpr_kernel(int64_t nl, double* __restrict__ R, int64_t ldr, double* __restrict__ C,
+                                    int64_t ldc, const double* __restrict__ theta, const double* __restrict__ dA,
+                                    const double* __restrict__ dB, int write_correction,
+                                    double* __restrict__ partial) {
+  __shared__ double red[32];
+  const int j = blockIdx.y, c = blockIdx.x;
+  const int64_t per = (nl + NCHUNK - 1) / NCHUNK;
+  const int64_t beg = (int64_t)c * per, end = min(nl, beg + per);
+  const double th = theta[j];
+  double s = 0.0;
+  for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
+    const double r = R[i + (int64_t)j * ldr] - th * C[i + (int64_t)j * ldc];
+    R[i + (int64_t)j * ldr] = r;
+    s = fma(r, r, s);
+    if (write_correction) {
+      const double den = th * (dB ? dB[i] : 1.0) - dA[i];  // davidson.f90:691,693 / :484, unguarded
+      C[i + (int64_t)j * ldc] = r / den;
+    }
+  }
+  s = warp_sum(s);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) red[wid] = s;
+  __syncthreads();
+  if (wid == 0) {
+    double x = lane < (blockDim.x >> 5) ? red[lane] : 0.0;
+    x = warp_sum(x);
+    if (lane == 0) partial[(size_t)j * NCHUNK + c] = x;
+  }
+}
+
+__global__ void fill_random_cols_kernel(double* X, int64_t ldx, int64_t nl, int64_t row0, const int* flags, int k,
+                                        uint64_t salt) {
+  for (int j = blockIdx.y; j < k; j += gridDim.y) {
+    if (!flags[j]) continue;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nl; i += (int64_t)gridDim.x * blockDim.x)
+      X[i + (int64_t)j * ldx] = 2.0 * uniform01(salt, (uint64_t)(row0 + i), (uint64_t)j) - 1.0;
+  }
+}
+
+__global__ void fill_random_kernel(double* X, size_t count, uint64_t salt) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (size_t)gridDim.x * blockDim.x)
+    X[e] = 2.0 * uniform01(salt, e, 0x5bd1e995ULL) - 1.0;
+}
+
+__global__ void unstage_allgather_kernel(const double* __restrict__ stage, int world, int64_t chunk, int64_t n, int b,
+                                         double* __restrict__ X, int64_t ldx) {
+  for (int j = blockIdx.y; j < b; j += gridDim.y)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = i / chunk, li = i - r * chunk;
+      X[i + (int64_t)j * ldx] = stage[(size_t)r * chunk * b + (size_t)j * chunk + li];
+    }
+}
+
+__global__ void stage_block_kernel(const double* __restrict__ X, int64_t ldx, int64_t nl, int64_t chunk, int b,
+                                   double* __restrict__ stage) {
+  for (int j = blockIdx.y; j < b; j += gridDim.y)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < chunk; i += (int64_t)gridDim.x * blockDim.x)
+      stage[(size_t)j * chunk + i] = (i < nl) ? X[i + (int64_t)j * ldx] : 0.0;
+}
+
+inline dim3 grid2(int64_t rows, int cols) {
+  const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(rows, 256), 4 * SMS));
+  const unsigned gy = (unsigned)std::max(1, std::min(cols, 65535));
+  return dim3(gx, gy);
+}
+inline int grid1(size_t count) {
+  return (int)std::max<size_t>(1, std::min<size_t>((count + 255) / 256, (size_t)8 * SMS));
+}
+
+}  // namespace
+
+#define LAUNCHED()  \
+  do {              \
+    CK_LAUNCH();    \
+    ++g_kernel_launches; \
+  } while (0)
+
+void fill_zero(cudaStream_t s, double* p, size_t count) {
+  if (!count) return;
+  fill_zero_kernel<<<grid1(count), 256, 0, s>>>(p, count);
+  LAUNCHED();
+}
+
+void copy_matrix(cudaStream_t s, int64_t rows, int64_t cols, const double* src, int64_t lds, double* dst,
+                 int64_t ldd) {
+  if (rows <= 0 || cols <= 0) return;
+  copy_matrix_kernel<<<grid1((size_t)rows * cols), 256, 0, s>>>(rows, cols, src, lds, dst, ldd);
+  LAUNCHED();
+}
+
+void gen_diag_dominant(cudaStream_t s, double* A, int64_t lda, int64_t nl, int64_t n, int64_t row0, double sparsity,
+                       int has_diag, double diag_val, uint64_t seed) {
+  if (nl <= 0) return;
+  dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(nl, 256), 64)),
+            (unsigned)std::min<int64_t>(n, 8 * SMS));
+  gen_diag_dominant_kernel<<<grid, 256, 0, s>>>(A, lda, nl, n, row0, sparsity, has_diag, diag_val, seed);
+  LAUNCHED();
+}
+
+void extract_diag(cudaStream_t s, const double* A, int64_t lda, int64_t nl, int64_t row0, double* out) {
+  if (nl <= 0) return;
+  extract_diag_kernel<<<grid1((size_t)nl), 256, 0, s>>>(A, lda, nl, row0, out);
+  LAUNCHED();
+}
+
+void topk_smallest(cudaStream_t s, const double* diag, const int64_t* gidx, int64_t count, int64_t row0, int k,
+                   double* out_val, int64_t* out_idx, int* status) {
+  topk_smallest_kernel<<<1, 1024, 0, s>>>(diag, gidx, count, row0, k, out_val, out_idx, status);
+  LAUNCHED();
+}
+
+void set_onehot(cudaStream_t s, double* V, int64_t ldv, int64_t nl, int64_t row0, const int64_t* idx, int k) {
+  set_onehot_kernel<<<1, 256, 0, s>>>(V, ldv, nl, row0, idx, k);
+  LAUNCHED();
+}
+
+void gather_columns(cudaStream_t s, const double* A, int64_t lda, int64_t nl, const int64_t* idx, int k, double* out,
+                    int64_t ldo) {
+  if (nl <= 0 || k <= 0) return;
+  gather_columns_kernel<<<grid2(nl, k), 256, 0, s>>>(A, lda, nl, idx, k, out, ldo);
+  LAUNCHED();
+}
+
+void col_norms2(cudaStream_t s, int64_t nl, int k, const double* X, int64_t ldx, double* partial, double* out) {
+  if (k <= 0) return;
+  col_norms2_stage1<<<dim3(NCHUNK, k), 256, 0, s>>>(nl, X, ldx, partial);
+  LAUNCHED();
+  col_reduce_stage2<<<(k + 127) / 128, 128, 0, s>>>(k, partial, out);
+  LAUNCHED();
+}
+
+void scale_cols_rsqrt(cudaStream_t s, int64_t nl, int k, double* X, int64_t ldx, const double* n2) {
+  if (nl <= 0 || k <= 0) return;
+  scale_cols_rsqrt_kernel<<<grid2(nl, k), 256, 0, s>>>(nl, k, X, ldx, n2);
+  LAUNCHED();
+}
+
+void residual_dpr(cudaStream_t s, int64_t nl, int k, double* R, int64_t ldr, double* C, int64_t ldc,
+                  const double* theta, const double* dA, const double* dB, bool write_correction, double* partial,
+                  double* n2out) {
+  if (k <= 0) return;
+  residual_dpr_kernel<<<dim3(NCHUNK, k), 256, 0, s>>>(nl, R, ldr, C, ldc, theta, dA, dB, write_correction ? 1 : 0,
+                                                      partial);
+  LAUNCHED();
+  col_reduce_stage2<<<(k + 127) / 128, 128, 0, s>>>(k, partial, n2out);
+  LAUNCHED();
+}
+
+void fill_random_cols(cudaStream_t s, double* X, int64_t ldx, int64_t nl, int64_t row0, const int* flags, int k,
+                      uint64_t salt) {
+  if (nl <= 0 || k <= 0) return;
+  fill_random_cols_kernel<<<grid2(nl, k), 256, 0, s>>>(X, ldx, nl, row0, flags, k, salt);
+  LAUNCHED();
+}
+
+void fill_random(cudaStream_t s, double* X, size_t count, uint64_t salt) {
+  if (!count) return;
+  fill_random_kernel<<<grid1(count), 256, 0, s>>>(X, count, salt);
+  LAUNCHED();
+}
+
+void unstage_allgather(cudaStream_t s, const double* stage, int world, int64_t chunk, int64_t n, int b, double* X,
+                       int64_t ldx) {
+  unstage_allgather_kernel<<<grid2(n, b), 256, 0, s>>>(stage, world, chunk, n, b, X, ldx);
+  LAUNCHED();
+}
+
+void stage_block(cudaStream_t s, const double* X, int64_t ldx, int64_t nl, int64_t chunk, int b, double* stage) {
+  stage_block_kernel<<<grid2(chunk, b), 256, 0, s>>>(X, ldx, nl, chunk, b, stage);
+  LAUNCHED();
+}
+
+}  // namespace dav

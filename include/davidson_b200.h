@@ -1,0 +1,210 @@
+/*
+ * davidson_b200.h -- C ABI of the B200-native Davidson eigensolver.
+ *
+ * This is the drop-in boundary: the entry points below are exactly what a Fortran
+ * `iso_c_binding` shim (fortran/davidson.f90 in this repo), a ctypes stub, or any other FFI for
+ * the reference's `davidson` / `array_utils` / `lapack_wrapper` modules would bind.  Citations
+ * are into NLESC-JCER/Fortran_Davidson (`src/...`).
+ *
+ * Conventions
+ *   - every matrix is column-major (Fortran order) IEEE binary64; `ld*` are leading dimensions
+ *   - every function returns 0 on success or a DAV_ERR_* code; dav_last_error() gives the text
+ *     (the reference prints + `error stop`s, lapack_wrapper.f90:395-408 -- the shim does that
+ *     with this text)
+ *   - host pointers are never retained after a call returns; a dav_solver_t owns device memory only
+ *   - there is NO CPU fallback: every entry point that computes fails with DAV_ERR_CUDA when no
+ *     sm_100 device is usable
+ */
+#ifndef DAVIDSON_B200_H
+#define DAVIDSON_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define DAV_VERSION 100
+
+/* error codes */
+enum {
+  DAV_OK = 0,
+  DAV_ERR_INVALID = 1,        /* bad argument (incl. unknown method; the reference leaves the
+                                 correction undefined there, davidson.f90:656-669) */
+  DAV_ERR_CUDA = 2,           /* CUDA runtime / no device */
+  DAV_ERR_NOT_POSDEF = 3,     /* projected second_matrix not positive definite (DSYGV info > n) */
+  DAV_ERR_NO_CONVERGENCE = 4, /* small dense solver did not converge (DSYEV info > 0) */
+  DAV_ERR_BASIS_TOO_LARGE = 5,/* expansion would exceed n columns (DORGQR info < 0 in the reference) */
+  DAV_ERR_COMM = 6,           /* NCCL */
+  DAV_ERR_STATE = 7           /* call order (e.g. solve before a matrix was set) */
+};
+
+/* correction methods (davidson.f90:61-64, :656-669) */
+enum { DAV_METHOD_DPR = 0, DAV_METHOD_GJD = 1 };
+
+/* built-in on-the-fly operators for the matrix-free path */
+enum {
+  DAV_OP_BENCHMARK_MTX = 0, /* benchmark_free.f90:38-63  compute_matrix_on_the_fly */
+  DAV_OP_IDENTITY = 1,      /* benchmark_free.f90:65-76  compute_stx_on_the_fly (identity) */
+  DAV_OP_TEST_MTX = 2,      /* tests/test_utils.f90:37-51 (same entries as 0) */
+  DAV_OP_TEST_STX = 3       /* tests/test_utils.f90:54-68,97-116 (sin variant, unit diagonal) */
+};
+
+/* block matvec implementations (diagnostics / parity tests) */
+enum { DAV_MATVEC_AUTO = 0, DAV_MATVEC_SIMT = 1, DAV_MATVEC_TMA_DMMA = 2 };
+
+const char* dav_last_error(void);
+int dav_version(void);
+/* number of usable CUDA devices (0 without a GPU; never fails) */
+int dav_device_count(void);
+
+/* =============================================================================================
+ * 1. Drop-in solver calls (host pointers in, host pointers out).
+ * ============================================================================================= */
+
+/* generalized_eigensolver_dense (davidson.f90:51-246), also `eigensolver` of README.md:20 when
+ * second_matrix == NULL.
+ *   matrix, second_matrix : n x n, column-major, intent(in); second_matrix may be NULL (optional)
+ *   method                : "DPR" or "GJD" (NUL terminated)
+ *   max_dim_sub           : <= 0 means "not present" (default 10*lowest, davidson.f90:115-119)
+ *   eigenvalues[lowest], eigenvectors[ldv x lowest] : outputs (first `lowest` Ritz pairs of the
+ *                           last Rayleigh-Ritz step, davidson.f90:186-187)
+ *   iters                 : iteration index at convergence, or max_iterations+1 plus the warning
+ *                           " Warning: Algorithm did not converge!!" (davidson.f90:232-235)       */
+int dav_generalized_eigensolver_dense(int64_t n, const double* matrix, int64_t lda, const double* second_matrix,
+                                      int64_t ldb, int lowest, const char* method, int max_iterations,
+                                      double tolerance, int max_dim_sub, double* eigenvalues, double* eigenvectors,
+                                      int64_t ldv, int* iters);
+
+/* Host callback of the matrix-free path: Y(n x b) = Op * X(n x b), both column-major with leading
+ * dimension n (the shape of `fun_matrix_gemv`, davidson.f90:317-325). */
+typedef void (*dav_gemv_fn)(const double* x, double* y, int64_t n, int64_t b, void* ctx);
+
+/* generalized_eigensolver_free (davidson.f90:277-460) with host callbacks.  Always generalized
+ * (fun_second_matrix_gemv is not optional, :327-335), `method` accepted and ignored (:428),
+ * convergence non-sticky (:416), *iters left untouched when not converged (:417).
+ * diag_matrix / diag_second_matrix may be NULL: they are then extracted by n operator
+ * applications like extract_diagonal_free (davidson.f90:490-523). */
+int dav_generalized_eigensolver_free(int64_t n, dav_gemv_fn fun_matrix_gemv, void* ctx_matrix,
+                                     dav_gemv_fn fun_second_matrix_gemv, void* ctx_second,
+                                     const double* diag_matrix, const double* diag_second_matrix, int lowest,
+                                     const char* method, int max_iterations, double tolerance, int max_dim_sub,
+                                     double* eigenvalues, double* ritz_vectors, int64_t ldv, int* iters);
+
+/* Same, with built-in device generators (DAV_OP_*) instead of callbacks: the operator entries are
+ * generated on the fly in registers, nothing n x n is ever stored. */
+int dav_generalized_eigensolver_free_builtin(int64_t n, int op_matrix, int op_second_matrix, int lowest,
+                                             const char* method, int max_iterations, double tolerance,
+                                             int max_dim_sub, double* eigenvalues, double* ritz_vectors,
+                                             int64_t ldv, int* iters);
+
+/* =============================================================================================
+ * 2. Device-resident handle API (the timed path): matrices live in HBM, row-block sharded over
+ *    the ranks of one node; only eigenpairs, flags and norms come back.
+ * ============================================================================================= */
+typedef struct dav_solver dav_solver_t;
+
+/* NCCL bootstrap: rank 0 fills a 128-byte id, the caller broadcasts it (e.g. torch.distributed). */
+int dav_get_unique_id(void* id128);
+int dav_create(dav_solver_t** h, int device);
+int dav_create_distributed(dav_solver_t** h, int device, int rank, int world_size, const void* id128);
+int dav_destroy(dav_solver_t* h);
+
+/* rows [row_begin, row_end) of an n-row matrix owned by `rank` of `world_size` (contiguous blocks,
+ * multiples of 128 rows except the last) -- pure host arithmetic, usable without a GPU. */
+int dav_partition_rows(int64_t n, int world_size, int rank, int64_t* row_begin, int64_t* row_end);
+
+/* which: 0 = matrix, 1 = second_matrix */
+/* generate_diagonal_dominant (array_utils.f90:86-113) on device with the counter-based stream
+ * shared with the oracle: a(i,j)=a(j,i)=sparsity*U(seed,min,max), a(i,i)=diag_val or i (1-based). */
+int dav_matrix_generate_diagonal_dominant(dav_solver_t* h, int which, int64_t n, double sparsity, int has_diag_val,
+                                          double diag_val, uint64_t seed);
+/* upload a host matrix (each rank copies its own row block) */
+int dav_matrix_upload(dav_solver_t* h, int which, int64_t n, const double* host_matrix, int64_t ld);
+/* matrix-free: built-in generator or host callback (diag may be NULL) */
+int dav_matrix_set_operator(dav_solver_t* h, int which, int64_t n, int op);
+int dav_matrix_set_callback(dav_solver_t* h, int which, int64_t n, dav_gemv_fn fn, void* ctx, const double* diag);
+int dav_matrix_clear(dav_solver_t* h, int which);
+/* copy the local row block back (row_end-row_begin rows x n columns, ld >= rows) -- parity tests */
+int dav_matrix_download(dav_solver_t* h, int which, double* host_rows, int64_t ld);
+
+/* solve with the matrices currently set.  Dense matrices -> dense semantics (sticky convergence,
+ * iters = max_iterations+1 when not converged); operators/callbacks -> free semantics.
+ * eigenvectors: full n x lowest on every rank (may be NULL to skip the device->host copy). */
+int dav_solve(dav_solver_t* h, int lowest, int method, int max_iterations, double tolerance, int max_dim_sub,
+              double* eigenvalues, double* eigenvectors, int64_t ldv, int* iters);
+
+typedef struct {
+  double solve_ms;          /* CUDA-event time of the last dav_solve (device work of the whole loop) */
+  double matvec_ms;         /* sum of block-matvec kernel time inside it (events on the solver stream) */
+  double matvec_bytes;      /* algorithmic bytes of those launches: 8*nl*n + 8*n*b + 8*nl*b each */
+  double matvec_flops;      /* 2*nl*n*b each */
+  int matvec_launches;      /* block-matvec launches (A and B count separately) */
+  int kernel_launches;      /* every kernel this library launched inside the solve */
+  int iterations;           /* outer iterations executed */
+  int trace_len;            /* entries valid in trace_* */
+  int trace_k[64];          /* basis width at each Rayleigh-Ritz step */
+  double trace_err[64];     /* largest residual norm among the `lowest` pairs at that step */
+  int last_matvec_b;        /* width of the last block */
+  double last_matvec_ms;    /* and its kernel time */
+  double rr_ms, orth_ms, resid_ms, proj_ms, init_ms; /* phase times (events) */
+} dav_stats_t;
+int dav_get_stats(dav_solver_t* h, dav_stats_t* out);
+
+/* knobs: DAV_MATVEC_* implementation of the block matvec */
+int dav_set_matvec_impl(dav_solver_t* h, int impl);
+
+/* Block matvec on the resident matrix: W(local rows x b) = M(local rows, :) * X(n x b).
+ * Host X in (ldx >= n), host W out (ldw >= local rows).  Parity-test entry. */
+int dav_block_matvec(dav_solver_t* h, int which, int64_t b, const double* x, int64_t ldx, double* w, int64_t ldw);
+/* Time `reps` launches of the block matvec kernel on resident data with CUDA events on the solver
+ * stream (X = deterministic pseudo-random block kept on device).  ms_out[reps]. */
+int dav_bench_block_matvec(dav_solver_t* h, int which, int64_t b, int reps, float* ms_out);
+
+/* =============================================================================================
+ * 3. array_utils / lapack_wrapper mirrors on device (host pointers in/out).
+ * ============================================================================================= */
+/* generate_diagonal_dominant (array_utils.f90:86-113); diag_val may be NULL ("not present") */
+int dav_generate_diagonal_dominant(int64_t m, double sparsity, const double* diag_val, uint64_t seed, double* arr,
+                                   int64_t ld);
+/* generate_preconditioner (array_utils.f90:136-160): n x dim_sub one-hot columns at the dim_sub
+ * smallest entries of diag, ascending, ties by index.  diag is NOT modified (the reference sorts
+ * it in place, a side effect no caller relies on). */
+int dav_generate_preconditioner(int64_t n, const double* diag, int dim_sub, double* precond, int64_t ld);
+/* norm (array_utils.f90:46-53) */
+int dav_norm(int64_t n, const double* vector, double* result);
+/* lapack_generalized_eigensolver (lapack_wrapper.f90:14-91): all eigenpairs ascending, upper
+ * triangle read; stx may be NULL.  Device Jacobi. */
+int dav_lapack_generalized_eigensolver(int dim, const double* mtx, const double* stx, double* eigenvalues,
+                                       double* eigenvectors);
+/* lapack_generalized_eigensolver_lowest (lapack_wrapper.f90:93-174) */
+int dav_lapack_generalized_eigensolver_lowest(int dim, const double* mtx, const double* stx, int lowest,
+                                              double* eigenvalues, double* eigenvectors);
+/* lapack_qr (lapack_wrapper.f90:176-236): orthonormal basis of the columns, in place (m >= n) */
+int dav_lapack_qr(int64_t m, int n, double* basis, int64_t ld);
+/* lapack_solver (lapack_wrapper.f90:238-277): symmetric solve arr * x = brr, x overwrites brr */
+int dav_lapack_solver(int n, const double* arr, double* brr);
+/* lapack_matmul (lapack_wrapper.f90:279-328): mtx = alpha * op(arr) * op(brr); shapes as stored */
+int dav_lapack_matmul(char transA, char transB, int64_t rows_a, int64_t cols_a, const double* arr, int64_t rows_b,
+                      int64_t cols_b, const double* brr, double alpha, double* mtx);
+/* lapack_matrix_vector (lapack_wrapper.f90:330-364) */
+int dav_lapack_matrix_vector(char transA, int64_t m, int64_t n, const double* mtx, const double* vector,
+                             double alpha, double* rs);
+/* lapack_sort (lapack_wrapper.f90:367-392): sorts vector in place ('I'/'D'), keys[i] = 1-based
+ * position of original element i in the sorted vector (ties: stable) */
+int dav_lapack_sort(char id, int64_t n, double* vector, int32_t* keys);
+/* free_matmul (davidson.f90:526-569) with a built-in generator: out = Op * array */
+int dav_free_matmul(int op, int64_t n, int64_t b, const double* array, double* out);
+/* column i (1-based) of a built-in operator: compute_matrix_on_the_fly(i, dim) */
+int dav_compute_on_the_fly(int op, int64_t i, int64_t dim, double* vector);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAVIDSON_B200_H */

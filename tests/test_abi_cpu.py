@@ -1,0 +1,66 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads without a GPU, exports every
+symbol include/davidson_b200.h declares, its pure-host helpers work, and compute entry points fail
+loudly (no CPU fallback) when no device is present."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import fortran_davidson_b200 as fd
+from fortran_davidson_b200._lib import SYMBOLS, DavidsonError
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "davidson_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(dav_[a-z0-9_]+)\s*\(", header)) - {"dav_gemv_fn"})
+    assert declared, "no declarations found"
+    L = fd.lib()
+    for name in declared:
+        assert hasattr(L, name), "missing export " + name
+    assert sorted(SYMBOLS) == declared
+    assert L.dav_version() == 100
+
+
+def test_partition_rows_tiles_the_matrix():
+    L = fd.lib()
+    for n in (1, 50, 127, 128, 1000, 20000, 100000, 2000000):
+        for world in (1, 2, 3, 4, 8):
+            prev_end = 0
+            for r in range(world):
+                b, e = C.c_int64(), C.c_int64()
+                assert L.dav_partition_rows(C.c_int64(n), world, r, C.byref(b), C.byref(e)) == 0
+                assert b.value == prev_end and e.value >= b.value
+                if world > 1 and e.value < n:
+                    assert (e.value - b.value) % 128 == 0
+                prev_end = e.value
+            assert prev_end == n
+    b, e = C.c_int64(), C.c_int64()
+    assert L.dav_partition_rows(C.c_int64(10), 2, 5, C.byref(b), C.byref(e)) != 0
+
+
+def test_no_cpu_fallback():
+    if fd.lib().dav_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(DavidsonError) as ei:
+        fd.generate_diagonal_dominant(8, 1e-4)
+    assert ei.value.code == 2
+    with pytest.raises(DavidsonError):
+        fd.generalized_eigensolver(np.eye(8), 2, "DPR", 10, 1e-8)
+    with pytest.raises(DavidsonError):
+        fd.DavidsonSolver()
+
+
+def test_package_does_not_import_oracle():
+    """The product must not route through the oracle: no file under fortran_davidson_b200/ mentions it."""
+    pkg = os.path.join(ROOT, "fortran_davidson_b200")
+    for dirpath, _dirs, files in os.walk(pkg):
+        if "_build" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f
