@@ -7,7 +7,7 @@
 //   * persistent grid, one CTA per SM, stream-K: the (row tile x k step) units are split evenly and
 //     contiguously over the CTAs; partially covered tiles go to a workspace and a tiny fixup kernel
 //     adds them in a fixed order (bit-reproducible, no atomics).
-//   * warp-specialised: warp 8 is the TMA producer, warps 0-7 consume.  A tiles arrive through a
+//   * warp-specialised: warp 8 is the TMA producer, warps 0-7 consume (each 32 rows x up to 32 columns).  A tiles arrive through a
 //     2D tensor map (box 16 rows x 16 columns, 128-byte swizzle) with mbarrier complete_tx; the X
 //     tile is pre-packed in fragment order so one 1D bulk copy per stage fetches it.
 //   * FP64 tensor-core math: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4).  tcgen05 has no FP64 kind, so
@@ -113,7 +113,7 @@ __global__ void pack_x_kernel(int64_t K, int64_t Kpad, int b, int bpad, const do
 }
 
 template <int NT, int WARPS_N>
-__global__ void __maxnreg__(224)
+__global__ void __launch_bounds__(THREADS, 1)
     matvec_kernel(const __grid_constant__ CUtensorMap tmapA, const Params p) {
   constexpr int WARPS_M = CONSUMERS / WARPS_N;
   constexpr int BM = WARPS_M * 32;
@@ -366,7 +366,7 @@ MatvecPlan* matvec_plan_create(const double* A, int64_t M, int64_t K, int64_t ld
   }
   const int bmax = (int)std::min<int64_t>(round_up(std::max(max_b, 8), 8), 128);
   p->Xp.alloc((size_t)round_up(K, BK) * bmax);
-  p->ws.alloc((size_t)p->num_sms * 2 * 256 * 64);
+  p->ws.alloc((size_t)p->num_sms * 2 * 256 * 32);  // BM x BPAD <= 8192 for every config
   return p;
 }
 
@@ -378,9 +378,11 @@ void matvec_dmma(cudaStream_t s, MatvecPlan* plan, int b, const double* X, int64
   for (int j0 = 0; j0 < b; j0 += 128) {
     const int bc = std::min(128, b - j0);
     int bpad = (int)round_up(bc, 8);
-    // config: one column warp up to 64 columns, two above
-    int warps_n = bpad <= 64 ? 1 : 2;
-    int nt = warps_n == 1 ? bpad / 8 : (bpad + 15) / 16;
+    // config: 8 consumer warps as (8/WN row warps) x (WN column warps); a warp owns 32 rows x NT*8 columns with
+    // NT <= 4 (the 9-warp CTA is granted at most 168 registers per thread)
+    //   bpad <= 32 : WN=1, BM=256   | bpad <= 64 : WN=2, BM=128   | bpad <= 128 : WN=4, BM=64
+    int warps_n = bpad <= 32 ? 1 : (bpad <= 64 ? 2 : 4);
+    int nt = (bpad + 8 * warps_n - 1) / (8 * warps_n);
     bpad = nt * warps_n * 8;
     if ((size_t)Kpad * bpad > plan->Xp.n) plan->Xp.alloc((size_t)Kpad * bpad);
     {
@@ -403,18 +405,17 @@ void matvec_dmma(cudaStream_t s, MatvecPlan* plan, int b, const double* X, int64
         case 1: CFG(1, 1); break;
         case 2: CFG(2, 1); break;
         case 3: CFG(3, 1); break;
-        case 4: CFG(4, 1); break;
-        case 5: CFG(5, 1); break;
-        case 6: CFG(6, 1); break;
-        case 7: CFG(7, 1); break;
-        default: CFG(8, 1); break;
+        default: CFG(4, 1); break;
+      }
+    } else if (warps_n == 2) {
+      switch (nt) {
+        case 3: CFG(3, 2); break;
+        default: CFG(4, 2); break;
       }
     } else {
       switch (nt) {
-        case 5: CFG(5, 2); break;
-        case 6: CFG(6, 2); break;
-        case 7: CFG(7, 2); break;
-        default: CFG(8, 2); break;
+        case 3: CFG(3, 4); break;
+        default: CFG(4, 4); break;
       }
     }
 #undef CFG

@@ -173,3 +173,144 @@ def solve_dense(A, lowest, method, max_iterations, tolerance, max_dim_sub=None, 
             k = 2 * lowest
     X = V @ Y[:, :lowest]
     return theta[:lowest].copy(), X, iters, np.array(trace_k), np.array(trace_err)
+
+
+# ------------------------------------------------------------------------------------------------
+# GJD correction as the device computes it (csrc/gjd.cu): for every Ritz pair (theta_j, u_j) solve the
+# projected correction equation
+#       (I - w u^T) (A - theta_j B) (I - u w^T) t = -r_j ,     w = B u_j  (w = u_j for the standard problem)
+# with diagonally preconditioned MINRES, all k columns in lock step so that A (and B) are streamed once
+# per inner iteration for the whole block.  For the standard problem this is exactly the operator the
+# reference builds, xs*ys*xs (davidson.f90:719-727); for the generalized problem the reference's literal
+# operator (I-uu^T)(A-theta B)(I-uu^T) has the exact solution t = -u/(1-u^T u) (no new direction) and only
+# converges through DSYSV's round-off, so the device solves the B-orthogonal (textbook) equation instead;
+# iteration counts agree with the oracle to +-1 (tests/test_device_model.py).
+# ------------------------------------------------------------------------------------------------
+GJD_RTOL = 1e-8
+GJD_MAXIT = 40
+GJD_DFLOOR = 1e-8
+
+
+def gjd_block_minres(mulA, mulB, theta, U, W, R, dA, dB, rtol=GJD_RTOL, maxit=GJD_MAXIT):
+    n, k = R.shape
+    dinv = 1.0 / np.maximum(np.abs(dA[:, None] - theta[None, :] * dB[:, None]), GJD_DFLOOR)
+    # projected preconditioner K~^-1 r = K^-1 r - z (w^T K^-1 r)/(w^T z), z = K^-1 w: keeps the Krylov vectors in
+    # the B-orthogonal complement of u, where the projected operator is non-singular
+    z = W * dinv
+    wz = (W * z).sum(axis=0)
+
+    def psolve(r):
+        y_ = r * dinv
+        return y_ - z * ((W * y_).sum(axis=0) / wz)
+
+    x = np.zeros((n, k))
+    r1 = -R.copy()
+    y = psolve(r1)
+    beta1sq = (r1 * y).sum(axis=0)
+    active = beta1sq > 0
+    beta1 = np.sqrt(np.where(active, beta1sq, 1.0))
+    beta = beta1.copy(); oldb = np.zeros(k); dbar = np.zeros(k); epsln = np.zeros(k)
+    phibar = beta1.copy(); cs = -np.ones(k); sn = np.zeros(k)
+    r2 = r1.copy(); w = np.zeros((n, k)); w2 = np.zeros((n, k))
+    its = 0
+    for itn in range(1, maxit + 1):
+        if not active.any():
+            break
+        its = itn
+        a = active
+        v = y / beta
+        d0 = (W * v).sum(axis=0)
+        P = v - U * d0
+        q = mulA(P) - (mulB(P) if mulB is not None else P) * theta
+        d1 = (U * q).sum(axis=0)
+        ynew = q - W * d1
+        if itn >= 2:
+            ynew = ynew - (beta / np.where(oldb != 0, oldb, 1.0)) * r1
+        alfa = (v * ynew).sum(axis=0)
+        ynew = ynew - (alfa / beta) * r2
+        r1n, r2n = r2, ynew
+        yn = psolve(r2n)
+        betasq = (r2n * yn).sum(axis=0)
+        bad = ~(betasq >= 0)
+        oldbn = beta
+        betan = np.sqrt(np.where(bad, 0.0, betasq))
+        oldeps = epsln
+        delta = cs * dbar + sn * alfa
+        gbar = sn * dbar - cs * alfa
+        epslnn = sn * betan
+        dbarn = -cs * betan
+        gamma = np.maximum(np.hypot(gbar, betan), 2.0 ** -52)
+        csn = gbar / gamma; snn = betan / gamma
+        phi = csn * phibar; phibarn = snn * phibar
+        w1 = w2; w2n = w
+        wn = (v - oldeps * w1 - delta * w2n) / gamma
+        xn = x + phi * wn
+        # masked commit (frozen columns keep their state)
+        def sel(new, old):
+            return np.where(a, new, old)
+        x = sel(xn, x); r1 = sel(r1n, r1); r2 = sel(r2n, r2); y = sel(yn, y); w = sel(wn, w); w2 = sel(w2n, w2)
+        oldb = sel(oldbn, oldb); beta = sel(betan, beta); epsln = sel(epslnn, epsln); dbar = sel(dbarn, dbar)
+        cs = sel(csn, cs); sn = sel(snn, sn); phibar = sel(phibarn, phibar)
+        active = a & ~bad & (betan > 0) & (phibar > rtol * beta1)
+    return x, its
+
+
+def solve_dense_gjd(A, lowest, max_iterations, tolerance, max_dim_sub=None, B=None):
+    """solve_dense with the GJD correction (dense path only, like the reference)."""
+    n = A.shape[0]
+    gev = B is not None
+    dA = np.diag(A).copy()
+    dB = np.diag(B).copy() if gev else np.ones(n)
+    k = 2 * lowest
+    max_dim = max_dim_sub if max_dim_sub else 10 * lowest
+    idx = np.argsort(dA, kind="stable")[:k]
+    V = np.zeros((n, k)); V[idx, np.arange(k)] = 1.0
+    AV = A @ V
+    BV = B @ V if gev else None
+    Ap = V.T @ AV
+    Bp = V.T @ BV if gev else None
+    has_conv = np.zeros(lowest, dtype=bool)
+    trace_k, inner = [], []
+    iters = max_iterations + 1
+    for it in range(1, max_iterations + 1):
+        theta, Y = sygv(Ap, Bp) if gev else jacobi_eigh(Ap)
+        W = (BV if gev else V) @ Y
+        U = V @ Y
+        R = AV @ Y - W * theta[None, :]
+        errs = np.sqrt((R[:, :lowest] ** 2).sum(axis=0))
+        trace_k.append(k)
+        has_conv |= errs < tolerance
+        X = U[:, :lowest]
+        if has_conv.all():
+            iters = it
+            break
+        if k <= max_dim:
+            C, nin = gjd_block_minres(lambda X: A @ X, (lambda X: B @ X) if gev else None, theta, U, W, R, dA, dB)
+            inner.append(nin)
+            Q = svqb(C, V)
+            AQ = A @ Q
+            Vn = np.hstack([V, Q])
+            Apn = np.zeros((2 * k, 2 * k)); Apn[:k, :k] = Ap
+            blk = Vn.T @ AQ
+            Apn[:, k:] = blk; Apn[k:, :k] = blk[:k, :].T
+            AV = np.hstack([AV, AQ]); Ap = Apn
+            if gev:
+                BQ = B @ Q
+                Bpn = np.zeros((2 * k, 2 * k)); Bpn[:k, :k] = Bp
+                blk = Vn.T @ BQ
+                Bpn[:, k:] = blk; Bpn[k:, :k] = blk[:k, :].T
+                BV = np.hstack([BV, BQ]); Bp = Bpn
+            V = Vn
+            k *= 2
+        else:
+            Yc = Y[:, :2 * lowest]
+            V = V @ Yc; AV = AV @ Yc
+            if gev:
+                BV = BV @ Yc
+                s, Um = jacobi_eigh(V.T @ V)
+                T = Um / np.sqrt(s)
+                V = V @ T; AV = AV @ T; BV = BV @ T
+                Bp = V.T @ BV
+            Ap = V.T @ AV
+            k = 2 * lowest
+    return theta[:lowest].copy(), X, iters, np.array(trace_k), inner

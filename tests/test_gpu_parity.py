@@ -130,7 +130,9 @@ def test_lapack_wrapper_mirrors():
     assert np.allclose(lw.lapack_solver(a, b), orc.lapack_solver(a, b), rtol=1e-9, atol=1e-11)
     p, qq = rng.standard_normal((700, 5)), rng.standard_normal((700, 4))
     assert np.allclose(lw.lapack_matmul("T", "N", p, qq), orc.lapack_matmul("T", "N", p, qq), rtol=1e-13, atol=1e-13)
-    assert np.allclose(lw.lapack_matmul("N", "T", p, qq), p @ qq.T, rtol=1e-13, atol=1e-13)
+    q3 = rng.standard_normal((3, 5))
+    assert np.allclose(lw.lapack_matmul("N", "T", p, q3), p @ q3.T, rtol=1e-13, atol=1e-13)
+    assert np.allclose(lw.lapack_matmul("T", "T", p, rng.standard_normal((6, 700))).shape, (5, 6))
     assert np.allclose(lw.lapack_matmul("N", "N", p.T, qq, 2.0), 2.0 * p.T @ qq, rtol=1e-13, atol=1e-12)
     assert np.allclose(lw.lapack_matrix_vector("N", a, b), a @ b, rtol=1e-13, atol=1e-13)
     assert np.allclose(lw.lapack_matrix_vector("T", p, qq[:, 0]), p.T @ qq[:, 0], rtol=1e-13, atol=1e-12)
