@@ -32,6 +32,7 @@ class Stats(C.Structure):
         ("iterations", C.c_int), ("trace_len", C.c_int), ("trace_k", C.c_int * 64), ("trace_err", C.c_double * 64),
         ("last_matvec_b", C.c_int), ("last_matvec_ms", C.c_double), ("rr_ms", C.c_double), ("orth_ms", C.c_double),
         ("resid_ms", C.c_double), ("proj_ms", C.c_double), ("init_ms", C.c_double),
+        ("gjd_inner_iterations", C.c_int),
     ]
 
 

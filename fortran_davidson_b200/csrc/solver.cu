@@ -395,11 +395,6 @@ void dav_solver::orthonormalize_block(double* Cblk, int b, int kold, double* des
   end_span(sp);
 }
 
-void dav_solver::gjd_correction(int k, bool gev) {
-  (void)k; (void)gev;
-  DAV_THROW(DAV_ERR_INVALID, "GJD correction is not available in this build");
-}
-
 int dav_solver::solve(int lowest, int method, int max_iterations, double tolerance, int max_dim_sub,
                       double* eigenvalues, double* eigenvectors, int64_t ldvec, int* iters) {
   CK(cudaSetDevice(device));

@@ -35,7 +35,8 @@ struct dav_solver {
   int kcap = 0;
   dav::DevBuf<double> V, AV, BV, R, C, T, Xfull, stage_s, stage_r;
   dav::DevBuf<double> Ap, Bp, Y, theta, G, U, sv, D, Tm, S1, S2, Z, jscratch, norms2, partial, gemm_ws, small;
-  dav::DevBuf<int> status, flags;
+  dav::DevBuf<int> status, flags, gjd_active;
+  dav::DevBuf<double> gjd_buf, gjd_st;
   dav::DevBuf<int64_t> idx, cand_idx;
   dav::DevBuf<double> cand_val;
   std::vector<double> host_x, host_y;  // callback staging

@@ -151,6 +151,7 @@ typedef struct {
   int last_matvec_b;        /* width of the last block */
   double last_matvec_ms;    /* and its kernel time */
   double rr_ms, orth_ms, resid_ms, proj_ms, init_ms; /* phase times (events) */
+  int gjd_inner_iterations; /* block-MINRES iterations of the GJD correction (each = one block matvec per matrix) */
 } dav_stats_t;
 int dav_get_stats(dav_solver_t* h, dav_stats_t* out);
 
