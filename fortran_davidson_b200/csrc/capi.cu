@@ -83,7 +83,7 @@ void eigensolve_dev(Ctx& c, int k, const double* mtx_h, const double* stx_h, dou
   const size_t kk = (size_t)k * k;
   DevBuf<double> S1, S2, U, sv, Tm, Z, Y, w, scratch;
   DevBuf<int> status;
-  S1.alloc(kk); Y.alloc(kk); w.alloc(k); scratch.alloc(2 * (size_t)(k + 2) * (k + 2)); status.alloc(1);
+  S1.alloc(kk); Y.alloc(kk); w.alloc(k); scratch.alloc(jacobi_scratch_doubles(k)); status.alloc(1);
   CK(cudaMemsetAsync(status.p, 0, sizeof(int), c.s));
   h2d(S1.p, mtx_h, kk, c.s);
   if (!stx_h) {

@@ -5,6 +5,8 @@
 // (davidson.f90:131,159,218,223,380-381,397,407-410,438; lapack_wrapper.f90:279-328).
 // 64x64x16 tiles, 256 threads, 4x4 register microtile; split-K partials are summed in a fixed
 // order by a second kernel, so results are bit-reproducible run to run.
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace dav {
@@ -133,8 +135,8 @@ void gemm(cudaStream_t s, bool transA, int64_t M, int64_t N, int64_t K, double a
   if (M <= 0 || N <= 0) return;
   const int64_t gx = ceil_div(M, BM), gy = ceil_div(N, BN);
   int splits = 1;
-  if (K > 4096 && gx * gy < 592) {  // long reduction, few output tiles: split K over the grid
-    splits = (int)std::min<int64_t>(ceil_div(592, gx * gy), ceil_div(K, 1024));
+  if (K > 1024 && gx * gy < 592) {  // long reduction, few output tiles: split K over the grid
+    splits = (int)std::min<int64_t>(ceil_div(592, gx * gy), ceil_div(K, 256));
     const size_t need = (size_t)M * (size_t)N;
     if (ws == nullptr || need == 0) splits = 1;
     else splits = (int)std::min<size_t>((size_t)splits, ws_doubles / need);

@@ -37,7 +37,9 @@ void free_column_builtin(cudaStream_t s, int op, int64_t n, int64_t col /*0-base
 // ---- smalldense.cu : k x k problems on one CTA ----------------------------------------------------
 // Two-sided Jacobi, round-robin parallel ordering.  S: k x k (ld k), upper triangle read, destroyed.
 // Y: k x k eigenvectors sorted by ascending eigenvalue w.  status: device int, set nonzero on failure
-// (1 = no convergence / NaN).  scratch: >= 2*(k+1)^2 doubles of global memory.
+// (1 = no convergence / NaN).  scratch: >= jacobi_scratch_doubles(k) doubles of global memory (rotation log of up
+// to 40 sweeps, or the S/V copies of the large-k path).
+inline size_t jacobi_scratch_doubles(int k) { return 44 * (size_t)(k + 2) * (size_t)(k + 2); }
 void jacobi_eigh(cudaStream_t s, int k, double* S, double* Y, double* w, double* scratch, int* status);
 // T(:,j) = U(:,j) / sqrt(sv[j]); status |= 2 if some sv[j] <= 0 (not positive definite)
 void scale_cols_rsqrt_checked(cudaStream_t s, int k, const double* U, const double* sv, double* T, int* status);

@@ -184,6 +184,186 @@ __global__ void __launch_bounds__(JT) jacobi_kernel(int k, const double* __restr
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Fast path (k <= ~165): the sweeps run on S alone (shared memory, one CTA, 2 barriers per round) and
+// every rotation (c, s) is logged; a second kernel replays the log on the rows of V = I, one row
+// per thread group, rows spread over several CTAs.  Same arithmetic as accumulating V inside the
+// sweeps, but V no longer sits on the critical path of the (latency-bound) rounds.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rr_pair(int kp, int r, int i, int& p, int& q) {
+  const int m = kp - 1;
+  int a, b;
+  if (i == 0) { a = kp - 1; b = r; }
+  else { a = (r + i) % m; b = (r - i + m) % m; }
+  p = min(a, b);
+  q = max(a, b);
+}
+
+__global__ void __launch_bounds__(512) jacobi_sweeps_kernel(int k, const double* __restrict__ S_in, double* __restrict__ w,
+                                                            int* __restrict__ rank_out, double2* __restrict__ rotlog,
+                                                            int* __restrict__ nrounds_out, int max_rounds,
+                                                            int* status) {
+  extern __shared__ __align__(16) double sm[];
+  const int kp = k + (k & 1), np = kp / 2, ld = kp + 1;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  double* red = sm;                                  // 32
+  double* rc = red + 32;                             // np
+  double* rs = rc + np;                              // np
+  double* wv = rs + np;                              // kp
+  int* rp = reinterpret_cast<int*>(wv + kp);         // np
+  int* rq = rp + np;                                 // np
+  const int nitems = np * (np + 1) / 2;
+  unsigned short* itab = reinterpret_cast<unsigned short*>(rq + np);  // 2 * nitems
+  size_t off = 32 + 2 * (size_t)np + kp + ((2 * (size_t)np) * sizeof(int) + 4 * (size_t)nitems + 7) / 8;
+  off = (off + 1) & ~(size_t)1;
+  double* S = sm + off;
+
+  // triangular work table: item e -> (iP <= iQ)
+  for (int e = tid; e < np * np; e += nt) {
+    const int iP = e % np, iQ = e / np;
+    if (iP <= iQ) {
+      const int idx = iQ * (iQ + 1) / 2 + iP;
+      itab[2 * idx] = (unsigned short)iP;
+      itab[2 * idx + 1] = (unsigned short)iQ;
+    }
+  }
+  // load, symmetrise from the upper triangle (DSYEV 'U'), find the scale
+  double mx = 0.0;
+  for (int e = tid; e < kp * kp; e += nt) {
+    const int i = e % kp, j = e / kp;
+    double v = 0.0;
+    if (i < k && j < k) v = (i <= j) ? S_in[i + (size_t)j * k] : S_in[j + (size_t)i * k];
+    S[i + j * ld] = v;
+    const double av = fabs(v);
+    mx = (av == av) ? fmax(mx, av) : 1.0e308 * 10.0;
+  }
+  mx = block_reduce_max(mx, red);
+  if (!(mx <= 1.0e300)) {
+    if (tid == 0) { atomicOr(status, 1); *nrounds_out = 0; }
+    for (int i = tid; i < k; i += nt) { rank_out[i] = i; w[i] = mx; }
+    return;
+  }
+  // exact power-of-two scaling so that squares cannot overflow / underflow
+  const int ex = (mx > 0.0) ? ilogb(mx) : 0;
+  const double sc = scalbn(1.0, -ex), usc = scalbn(1.0, ex);
+  double part = 0.0;
+  for (int e = tid; e < kp * kp; e += nt) {
+    const int i = e % kp, j = e / kp;
+    const double v = S[i + j * ld] * sc;
+    S[i + j * ld] = v;
+    part += v * v;
+  }
+  const double normF = sqrt(block_reduce_sum(part, red));
+  const double abs_thr = EPS * normF / (16.0 * kp);
+
+  const int m = kp - 1;
+  int round = 0;
+  for (int sweep = 0; sweep < MAX_SWEEPS; ++sweep) {
+    int rotated = 0;
+    for (int r = 0; r < m; ++r, ++round) {
+      if (tid < np) {
+        int p, q;
+        rr_pair(kp, r, tid, p, q);
+        double c = 1.0, s = 0.0;
+        if (q < k) {
+          const double apq = S[p + q * ld], app = S[p + p * ld], aqq = S[q + q * ld];
+          const double aa = fabs(apq);
+          if (aa > abs_thr && aa > EPS * sqrt(fabs(app) * fabs(aqq))) {
+            // t = sign(tau) / (|tau| + sqrt(1 + tau^2)), tau = (aqq - app) / (2 apq), without forming tau
+            const double a = aqq - app, b = 2.0 * apq;
+            const double rr = sqrt(a * a + b * b);
+            const double t = b / (a + copysign(rr, a));
+            c = rsqrt(1.0 + t * t);
+            s = t * c;
+            rotated = 1;
+          }
+        }
+        rc[tid] = c; rs[tid] = s; rp[tid] = p; rq[tid] = q;
+        if (round < max_rounds) rotlog[(size_t)round * np + tid] = make_double2(c, s);
+      }
+      __syncthreads();
+      for (int e = tid; e < nitems; e += nt) {
+        const int iP = itab[2 * e], iQ = itab[2 * e + 1];
+        const double sP = rs[iP], sQ = rs[iQ];
+        if (sP == 0.0 && sQ == 0.0) continue;
+        const double cP = rc[iP], cQ = rc[iQ];
+        const int p1 = rp[iP], q1 = rq[iP], p2 = rp[iQ], q2 = rq[iQ];
+        if (iP == iQ) {
+          const double apq = S[p1 + q1 * ld], app = S[p1 + p1 * ld], aqq = S[q1 + q1 * ld];
+          const double t = sP / cP;
+          S[p1 + p1 * ld] = app - t * apq;
+          S[q1 + q1 * ld] = aqq + t * apq;
+          S[p1 + q1 * ld] = 0.0;
+          S[q1 + p1 * ld] = 0.0;
+        } else {
+          const double m00 = S[p1 + p2 * ld], m01 = S[p1 + q2 * ld], m10 = S[q1 + p2 * ld], m11 = S[q1 + q2 * ld];
+          const double r00 = cP * m00 - sP * m10, r01 = cP * m01 - sP * m11;
+          const double r10 = sP * m00 + cP * m10, r11 = sP * m01 + cP * m11;
+          const double n00 = cQ * r00 - sQ * r01, n01 = sQ * r00 + cQ * r01;
+          const double n10 = cQ * r10 - sQ * r11, n11 = sQ * r10 + cQ * r11;
+          S[p1 + p2 * ld] = n00; S[p2 + p1 * ld] = n00;
+          S[p1 + q2 * ld] = n01; S[q2 + p1 * ld] = n01;
+          S[q1 + p2 * ld] = n10; S[p2 + q1 * ld] = n10;
+          S[q1 + q2 * ld] = n11; S[q2 + q1 * ld] = n11;
+        }
+      }
+      __syncthreads();
+    }
+    const int any = __syncthreads_or(rotated);
+    if (!any) break;
+    if (sweep == MAX_SWEEPS - 1 && tid == 0) atomicOr(status, 1);
+  }
+  if (round > max_rounds && tid == 0) atomicOr(status, 1);
+
+  for (int i = tid; i < k; i += nt) wv[i] = S[i + i * ld];
+  __syncthreads();
+  for (int i = tid; i < k; i += nt) {
+    const double wi = wv[i];
+    int rank = 0;
+    for (int j = 0; j < k; ++j) {
+      const double wj = wv[j];
+      rank += (wj < wi) || (wj == wi && j < i);
+    }
+    if (!(wi == wi)) { atomicOr(status, 1); rank = i; }
+    rank_out[i] = rank;
+    w[rank] = wi * usc;
+  }
+  if (tid == 0) *nrounds_out = min(round, max_rounds);
+}
+
+// Replays the rotation log on the rows of V = I: CTA = 32 rows x 8 lanes-per-row groups (256 threads).
+constexpr int VROWS = 32, VPARTS = 8;
+__global__ void __launch_bounds__(VROWS * VPARTS) jacobi_vectors_kernel(int k, const double2* __restrict__ rotlog,
+                                                                      const int* __restrict__ nrounds_in,
+                                                                      const int* __restrict__ rank,
+                                                                      double* __restrict__ Y) {
+  extern __shared__ __align__(16) double sm[];
+  const int kp = k + (k & 1), np = kp / 2, ld = kp + 1, m = kp - 1;
+  const int lrow = threadIdx.x % VROWS, part = threadIdx.x / VROWS;
+  const int row = blockIdx.x * VROWS + lrow;
+  double* vr = sm + (size_t)lrow * ld;
+  for (int j = part; j < kp; j += VPARTS) vr[j] = (j == row) ? 1.0 : 0.0;
+  __syncthreads();
+  const int nrounds = *nrounds_in;
+  for (int round = 0; round < nrounds; ++round) {
+    const int r = round % m;
+    const double2* rl = rotlog + (size_t)round * np;
+    for (int i = part; i < np; i += VPARTS) {
+      const double2 cs = __ldg(rl + i);
+      if (cs.y == 0.0) continue;
+      int p, q;
+      rr_pair(kp, r, i, p, q);
+      const double vp = vr[p], vq = vr[q];
+      vr[p] = cs.x * vp - cs.y * vq;
+      vr[q] = cs.y * vp + cs.x * vq;
+    }
+    __syncthreads();
+  }
+  if (row < k)
+    for (int j = part; j < k; j += VPARTS) Y[row + (size_t)rank[j] * k] = vr[j];
+}
+
 __global__ void scale_cols_rsqrt_checked_kernel(int k, const double* __restrict__ U, const double* __restrict__ sv,
                                                 double* __restrict__ T, int* status) {
   for (int e = threadIdx.x; e < k * k; e += blockDim.x) {
@@ -293,16 +473,44 @@ __global__ void invert_upper_kernel(int k, const double* __restrict__ R, int64_t
 void jacobi_eigh(cudaStream_t s, int k, double* S, double* Y, double* w, double* scratch, int* status) {
   if (k <= 0) return;
   const int kp = k + (k & 1), np = kp / 2;
-  size_t small = 32 + 2 * (size_t)np + kp + ((2 * (size_t)np + kp) * sizeof(int) + 7) / 8;
-  small = (small + 1) & ~(size_t)1;
-  const size_t big = (size_t)kp * kp;
   static int max_smem = -1;
   if (max_smem < 0) {
     int dev = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     CK(cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CK(cudaFuncSetAttribute(jacobi_sweeps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CK(cudaFuncSetAttribute(jacobi_vectors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   }
+  // ---- fast path: S in shared memory, rotations logged, V replayed by a second kernel
+  {
+    const int nitems = np * (np + 1) / 2;
+    size_t small = 32 + 2 * (size_t)np + kp + ((2 * (size_t)np) * sizeof(int) + 4 * (size_t)nitems + 7) / 8;
+    small = (small + 1) & ~(size_t)1;
+    const size_t need = (small + (size_t)kp * (kp + 1)) * sizeof(double);
+    // scratch layout: [rotation log: max_rounds * np double2][rank: k ints][nrounds: 1 int]
+    const size_t scratch_doubles = jacobi_scratch_doubles(k);
+    const size_t tail = ((size_t)k + 2) / 2 + 2;  // doubles reserved for the int arrays
+    const int max_rounds = (int)std::min<size_t>((scratch_doubles - tail) / (2 * (size_t)np), (size_t)MAX_SWEEPS * (kp - 1));
+    if (need <= (size_t)max_smem && max_rounds >= 8 * (kp - 1)) {
+      double2* rotlog = reinterpret_cast<double2*>(scratch);
+      int* rank = reinterpret_cast<int*>(scratch + scratch_doubles - tail);
+      int* nrounds = rank + k;
+      const int threads = kp <= 32 ? 128 : (kp <= 64 ? 256 : 512);
+      jacobi_sweeps_kernel<<<1, threads, need, s>>>(k, S, w, rank, rotlog, nrounds, max_rounds, status);
+      CK_LAUNCH();
+      ++g_kernel_launches;
+      const size_t vsm = (size_t)VROWS * (kp + 1) * sizeof(double);
+      jacobi_vectors_kernel<<<(k + VROWS - 1) / VROWS, VROWS * VPARTS, vsm, s>>>(k, rotlog, nrounds, rank, Y);
+      CK_LAUNCH();
+      ++g_kernel_launches;
+      return;
+    }
+  }
+  // ---- general path (large k): S and/or V in L2-resident global scratch
+  size_t small = 32 + 2 * (size_t)np + kp + ((2 * (size_t)np + kp) * sizeof(int) + 7) / 8;
+  small = (small + 1) & ~(size_t)1;
+  const size_t big = (size_t)kp * kp;
   const size_t cap = (size_t)max_smem / sizeof(double);
   int s_in = 0, v_in = 0;
   size_t doubles = small;

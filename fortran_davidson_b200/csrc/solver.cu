@@ -283,7 +283,7 @@ void dav_solver::alloc_work(int lowest, int kcap_) {
   Ap.alloc(kk); Bp.alloc(kk); Y.alloc(kk); G.alloc(kk); U.alloc(kk); Tm.alloc(kk); S1.alloc(kk); S2.alloc(kk);
   Z.alloc(kk);
   theta.alloc(kcap); sv.alloc(kcap); D.alloc(kcap); norms2.alloc(kcap);
-  jscratch.alloc(2 * (size_t)(kcap + 2) * (kcap + 2));
+  jscratch.alloc(jacobi_scratch_doubles(kcap));
   partial.alloc((size_t)kcap * 64);
   gemm_ws.alloc(std::max<size_t>(kk * 64, (size_t)1 << 22));
   small.alloc(16);

@@ -44,3 +44,30 @@ def test_model_parity_with_oracle(name, golden_cases):
     for j in range(g["lowest"]):
         s = np.sign(X[:, j] @ r.eigenvectors[:, j])
         assert np.abs(s * X[:, j] - r.eigenvectors[:, j]).max() < 1e-8
+
+
+GJD_CASES = ["matrix_txt_GJD", "readme_std_GJD", "readme_gev_GJD", "test_dense_numpy_std_GJD",
+             "test_dense_numpy_gen_GJD", "main_f90_GJD"]
+
+
+@pytest.mark.parametrize("name", GJD_CASES)
+def test_model_gjd_parity_with_oracle(name, golden_cases):
+    """GJD as the device computes it (block MINRES on the projected correction equation): same outer iteration count
+    (+-1) and eigenvalues as the reference's dense DSYSV solve."""
+    g = golden_cases[name]
+    A, B = case_inputs(name)
+    ev, X, iters, tk, inner = dm.solve_dense_gjd(A, g["lowest"], g["max_iterations"], g["tolerance"], g["max_dim_sub"], B)
+    assert abs(iters - g["iters"]) <= 1
+    assert np.abs(ev - np.array(g["eigenvalues"])).max() / np.abs(ev).max() < 1e-10
+    assert max(inner) <= dm.GJD_MAXIT
+
+
+def test_model_gjd_harder_cases():
+    for (n, sp, L, md, tol) in [(600, 1e-2, 3, 10, 1e-10), (1000, 5e-2, 4, 40, 1e-8)]:
+        A = orc.generate_diagonal_dominant(n, sp, seed=0)
+        B = orc.generate_diagonal_dominant(n, sp, 1.0, seed=1)
+        for Bm in (None, B):
+            r = orc.generalized_eigensolver(A, L, "GJD", 100, tol, md, Bm)
+            ev, X, iters, tk, inner = dm.solve_dense_gjd(A, L, 100, tol, md, Bm)
+            assert abs(iters - r.iters) <= 1
+            assert np.abs(ev - r.eigenvalues).max() / np.abs(ev).max() < 1e-10

@@ -168,6 +168,44 @@ def test_dense_dropin_parity(name, golden_cases):
     assert np.allclose(ev, g["eigh"])  # the reference's own acceptance check (test_davidson.py:39-40)
 
 
+DENSE_GJD = ["matrix_txt_GJD", "readme_std_GJD", "readme_gev_GJD", "test_dense_numpy_std_GJD",
+             "test_dense_numpy_gen_GJD", "main_f90_GJD"]
+
+
+@pytest.mark.parametrize("name", DENSE_GJD)
+def test_dense_gjd_parity(name, golden_cases):
+    """GJD on device (block MINRES on the projected correction equation) against the reference's O(n^3) DSYSV solve."""
+    g = golden_cases[name]
+    A, B = case_inputs(name)
+    ev, vec, iters = fd.generalized_eigensolver(A, g["lowest"], "GJD", g["max_iterations"], g["tolerance"],
+                                                g["max_dim_sub"], B)
+    assert abs(iters - g["iters"]) <= 1
+    r = orc.generalized_eigensolver(A, g["lowest"], "GJD", g["max_iterations"], g["tolerance"], g["max_dim_sub"], B)
+    _check_pairs(A, B, ev, vec, r.eigenvalues, r.eigenvectors, g["tolerance"])
+    assert np.allclose(ev, g["eigh"])
+    # test_dense_properties.f90:25-26: both methods give the same eigenvalues
+    ev2, _, _ = fd.generalized_eigensolver(A, g["lowest"], "DPR", g["max_iterations"], g["tolerance"], g["max_dim_sub"], B)
+    assert np.linalg.norm(ev - ev2) < 1e-8
+
+
+def test_dense_gjd_larger():
+    for (n, sp, L, md, tol) in [(600, 1e-2, 3, 10, 1e-10), (1000, 5e-2, 4, 40, 1e-8)]:
+        A = orc.generate_diagonal_dominant(n, sp, seed=0)
+        B = orc.generate_diagonal_dominant(n, sp, 1.0, seed=1)
+        for Bm in (None, B):
+            r = orc.generalized_eigensolver(A, L, "GJD", 100, tol, md, Bm)
+            s = fd.DavidsonSolver()
+            s.upload(0, A)
+            if Bm is not None:
+                s.upload(1, Bm)
+            ev, vec, iters = s.solve(L, "GJD", 100, tol, md)
+            st = s.stats()
+            assert abs(iters - r.iters) <= 1, (n, Bm is not None, iters, r.iters)
+            assert np.abs(ev - r.eigenvalues).max() / np.abs(ev).max() < EV_RTOL
+            assert 0 < st.gjd_inner_iterations <= 40 * iters
+            s.close()
+
+
 @pytest.mark.parametrize("impl", [dv.MATVEC_SIMT, dv.MATVEC_TMA_DMMA])
 @pytest.mark.parametrize("name", ["readme_gev_DPR", "collapse_n2000_DPR", "collapse_n1000_gev_DPR"])
 def test_dense_handle_trace(name, impl, golden_cases):
