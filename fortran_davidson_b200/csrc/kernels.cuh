@@ -55,6 +55,9 @@ void symmetrize_from_upper(cudaStream_t s, int k, double* S, int64_t ld);
 void max_abs_dev(cudaStream_t s, int rows, int cols, const double* G, int64_t ld, bool minus_identity, double* out);
 // Cholesky (upper, G = R^T R) in place on one CTA; status |= 2 when not positive definite
 void cholesky_upper(cudaStream_t s, int k, double* G, int64_t ld, int* status);
+// G (b x b, ld b, only read) = R^T R; T <- R^-1 (dense, upper).  flag[0] (device double) <- 1.0 if a pivot is not
+// safely positive, else 0.0.  Returns false (nothing launched) when b is too large for shared memory.
+bool chol_inv_upper(cudaStream_t s, int b, const double* G, double* T, double* flag);
 // Rinv = inverse of the upper triangular R (k x k)
 void invert_upper(cudaStream_t s, int k, const double* R, int64_t ld, double* Rinv);
 

@@ -269,11 +269,14 @@ __global__ void __launch_bounds__(512) jacobi_sweeps_kernel(int k, const double*
         if (q < k) {
           const double apq = S[p + q * ld], app = S[p + p * ld], aqq = S[q + q * ld];
           const double aa = fabs(apq);
-          if (aa > abs_thr && aa > EPS * sqrt(fabs(app) * fabs(aqq))) {
-            // t = sign(tau) / (|tau| + sqrt(1 + tau^2)), tau = (aqq - app) / (2 apq), without forming tau
+          if (aa > abs_thr && aa * aa > (EPS * EPS) * fabs(app * aqq)) {
+            // t = sign(tau) / (|tau| + sqrt(1 + tau^2)), tau = (aqq - app) / (2 apq), without forming tau;
+            // rsqrt / reciprocal instead of sqrt / divide (the 2x2 block is transformed with the general formulas
+            // below, so the similarity stays orthogonal to round-off whatever the last bits of t are)
             const double a = aqq - app, b = 2.0 * apq;
-            const double rr = sqrt(a * a + b * b);
-            const double t = b / (a + copysign(rr, a));
+            const double h2 = a * a + b * b;
+            const double rr = h2 * rsqrt(h2);
+            const double t = b * __drcp_rn(a + copysign(rr, a));
             c = rsqrt(1.0 + t * t);
             s = t * c;
             rotated = 1;
@@ -291,11 +294,12 @@ __global__ void __launch_bounds__(512) jacobi_sweeps_kernel(int k, const double*
         const int p1 = rp[iP], q1 = rq[iP], p2 = rp[iQ], q2 = rq[iQ];
         if (iP == iQ) {
           const double apq = S[p1 + q1 * ld], app = S[p1 + p1 * ld], aqq = S[q1 + q1 * ld];
-          const double t = sP / cP;
-          S[p1 + p1 * ld] = app - t * apq;
-          S[q1 + q1 * ld] = aqq + t * apq;
-          S[p1 + q1 * ld] = 0.0;
-          S[q1 + p1 * ld] = 0.0;
+          const double cc = cP * cP, ss = sP * sP, cs2 = 2.0 * cP * sP;
+          S[p1 + p1 * ld] = cc * app - cs2 * apq + ss * aqq;
+          S[q1 + q1 * ld] = ss * app + cs2 * apq + cc * aqq;
+          const double off = cP * sP * (app - aqq) + (cc - ss) * apq;  // ~ eps * |apq|: annihilated up to round-off
+          S[p1 + q1 * ld] = off;
+          S[q1 + p1 * ld] = off;
         } else {
           const double m00 = S[p1 + p2 * ld], m01 = S[p1 + q2 * ld], m10 = S[q1 + p2 * ld], m11 = S[q1 + q2 * ld];
           const double r00 = cP * m00 - sP * m10, r01 = cP * m01 - sP * m11;
@@ -332,33 +336,36 @@ __global__ void __launch_bounds__(512) jacobi_sweeps_kernel(int k, const double*
   if (tid == 0) *nrounds_out = min(round, max_rounds);
 }
 
-// Replays the rotation log on the rows of V = I: CTA = 32 rows x 8 lanes-per-row groups (256 threads).
-constexpr int VROWS = 32, VPARTS = 8;
+// Replays the rotation log on the rows of V = I.  A warp owns 2 rows x 16 lanes per row: the rotations of one
+// round touch disjoint column pairs, so the 16 lanes of a row work independently and only a __syncwarp
+// separates rounds.  CTA = 8 warps = 16 rows.
+constexpr int VROWS = 16, VPARTS = 16;
 __global__ void __launch_bounds__(VROWS * VPARTS) jacobi_vectors_kernel(int k, const double2* __restrict__ rotlog,
                                                                       const int* __restrict__ nrounds_in,
                                                                       const int* __restrict__ rank,
                                                                       double* __restrict__ Y) {
   extern __shared__ __align__(16) double sm[];
   const int kp = k + (k & 1), np = kp / 2, ld = kp + 1, m = kp - 1;
-  const int lrow = threadIdx.x % VROWS, part = threadIdx.x / VROWS;
+  const int lrow = threadIdx.x / VPARTS, part = threadIdx.x % VPARTS;  // lanes 0-15: one row, 16-31: the next
   const int row = blockIdx.x * VROWS + lrow;
   double* vr = sm + (size_t)lrow * ld;
   for (int j = part; j < kp; j += VPARTS) vr[j] = (j == row) ? 1.0 : 0.0;
-  __syncthreads();
+  __syncwarp();
   const int nrounds = *nrounds_in;
   for (int round = 0; round < nrounds; ++round) {
     const int r = round % m;
     const double2* rl = rotlog + (size_t)round * np;
     for (int i = part; i < np; i += VPARTS) {
       const double2 cs = __ldg(rl + i);
-      if (cs.y == 0.0) continue;
-      int p, q;
-      rr_pair(kp, r, i, p, q);
-      const double vp = vr[p], vq = vr[q];
-      vr[p] = cs.x * vp - cs.y * vq;
-      vr[q] = cs.y * vp + cs.x * vq;
+      if (cs.y != 0.0) {
+        int p, q;
+        rr_pair(kp, r, i, p, q);
+        const double vp = vr[p], vq = vr[q];
+        vr[p] = cs.x * vp - cs.y * vq;
+        vr[q] = cs.y * vp + cs.x * vq;
+      }
     }
-    __syncthreads();
+    __syncwarp();
   }
   if (row < k)
     for (int j = part; j < k; j += VPARTS) Y[row + (size_t)rank[j] * k] = vr[j];
@@ -455,6 +462,70 @@ __global__ void __launch_bounds__(1024) cholesky_upper_kernel(int k, double* G, 
   }
 }
 
+
+// Upper Cholesky factor G = R^T R and its inverse, one CTA, both triangles packed in shared memory
+// ((i,j), i <= j, at i + j(j+1)/2).  T <- R^-1 (dense b x b, zero below the diagonal).  flag[0] = 1.0 when a
+// pivot is not safely positive (the caller then falls back to the SVQB transform), else 0.0.  G is only read.
+__global__ void __launch_bounds__(512) chol_inv_upper_kernel(int b, const double* __restrict__ G, double* __restrict__ T,
+                                                             double* __restrict__ flag) {
+  extern __shared__ __align__(16) double sm[];
+  const int tri = b * (b + 1) / 2;
+  double* R = sm;
+  double* X = sm + tri;
+  double* d0 = X + tri;
+  __shared__ int bad;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) bad = 0;
+  for (int e = tid; e < b * b; e += nt) {
+    const int i = e % b, j = e / b;
+    if (i <= j) R[i + j * (j + 1) / 2] = G[i + (size_t)j * b];
+    if (i == j) d0[i] = G[i + (size_t)j * b];
+  }
+  __syncthreads();
+  for (int j = 0; j < b; ++j) {
+    const double d = R[j + j * (j + 1) / 2];
+    // pivot must stay well above the round-off of the eliminations (cond(G) < ~1e12)
+    if (!(d > 1e-12 * fabs(d0[j])) || !(d0[j] > 0.0)) {
+      if (tid == 0) bad = 1;
+      break;  // uniform: every thread reads the same d
+    }
+    const double rinv = rsqrt(d);
+    __syncthreads();  // everyone has read the pivot
+    for (int i = j + tid; i < b; i += nt) {
+      const int idx = j + i * (i + 1) / 2;
+      R[idx] = (i == j) ? d * rinv : R[idx] * rinv;
+    }
+    __syncthreads();
+    const int rem = b - j - 1;
+    for (int e = tid; e < rem * rem; e += nt) {
+      const int a = j + 1 + e % rem, c = j + 1 + e / rem;
+      if (a <= c) R[a + c * (c + 1) / 2] -= R[j + a * (a + 1) / 2] * R[j + c * (c + 1) / 2];
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (bad) {
+    if (tid == 0) flag[0] = 1.0;
+    return;
+  }
+  // X = R^-1, column j by thread j (back substitution)
+  for (int j = tid; j < b; j += nt) {
+    const int cj = j * (j + 1) / 2;
+    X[j + cj] = 1.0 / R[j + cj];
+    for (int i = j - 1; i >= 0; --i) {
+      double acc = 0.0;
+      for (int l = i + 1; l <= j; ++l) acc = fma(R[i + l * (l + 1) / 2], X[l + cj], acc);
+      X[i + cj] = -acc / R[i + i * (i + 1) / 2];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < b * b; e += nt) {
+    const int i = e % b, j = e / b;
+    T[e] = (i <= j) ? X[i + j * (j + 1) / 2] : 0.0;
+  }
+  if (tid == 0) flag[0] = 0.0;
+}
+
 __global__ void invert_upper_kernel(int k, const double* __restrict__ R, int64_t ld, double* __restrict__ X) {
   // column j of X solves R x = e_j (x_i = 0 for i > j), back substitution
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < k; j += gridDim.x * blockDim.x) {
@@ -496,7 +567,7 @@ void jacobi_eigh(cudaStream_t s, int k, double* S, double* Y, double* w, double*
       double2* rotlog = reinterpret_cast<double2*>(scratch);
       int* rank = reinterpret_cast<int*>(scratch + scratch_doubles - tail);
       int* nrounds = rank + k;
-      const int threads = kp <= 32 ? 128 : (kp <= 64 ? 256 : 512);
+      const int threads = kp <= 32 ? 128 : (kp <= 64 ? 256 : 512);  // __launch_bounds__(512)
       jacobi_sweeps_kernel<<<1, threads, need, s>>>(k, S, w, rank, rotlog, nrounds, max_rounds, status);
       CK_LAUNCH();
       ++g_kernel_launches;
@@ -556,6 +627,23 @@ void cholesky_upper(cudaStream_t s, int k, double* G, int64_t ld, int* status) {
   cholesky_upper_kernel<<<1, 1024, 0, s>>>(k, G, ld, status);
   CK_LAUNCH();
   ++g_kernel_launches;
+}
+
+bool chol_inv_upper(cudaStream_t s, int b, const double* G, double* T, double* flag) {
+  static int max_smem = -1;
+  if (max_smem < 0) {
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    CK(cudaFuncSetAttribute(chol_inv_upper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 1024));
+  }
+  const size_t bytes = ((size_t)b * (b + 1) + b) * sizeof(double);
+  if (bytes > (size_t)max_smem - 1024) return false;
+  const int threads = b <= 32 ? 128 : (b <= 64 ? 256 : 512);
+  chol_inv_upper_kernel<<<1, threads, bytes, s>>>(b, G, T, flag);
+  CK_LAUNCH();
+  ++g_kernel_launches;
+  return true;
 }
 
 void invert_upper(cudaStream_t s, int k, const double* R, int64_t ld, double* Rinv) {

@@ -191,7 +191,7 @@ void dav_solver::ensure_diag(int which) {
 
 void dav_solver::ensure_plan(int which, int max_b) {
   Matrix& m = mat[which];
-  if (m.kind != DENSE || m.plan) return;
+  if (m.kind != DENSE || m.plan || nl <= 0) return;
   if (matvec_impl == DAV_MATVEC_SIMT) return;
   if (!matvec_dmma_supported()) {
     if (matvec_impl == DAV_MATVEC_TMA_DMMA) DAV_THROW(DAV_ERR_CUDA, "TMA tensor maps unavailable from this driver");
@@ -357,9 +357,11 @@ void dav_solver::project_new_block(int which, int kold, int b) {
 }
 
 // Replaces lapack_qr on [V, C] (davidson.f90:210-213): V is already orthonormal, so only the new block is
-// touched: normalise columns, then repeat { C -= V (V^T C);  G = C^T C;  C <- C * (D U S^-1/2) } (SVQB)
-// until a pass starts from an already orthonormal block.  Rank-deficient directions (S below threshold)
-// are refilled with pseudo-random vectors, which is what Householder QR effectively returns for them.
+// touched: normalise columns, then repeat { C -= V (V^T C);  G = C^T C;  C <- C * T } until a pass starts from
+// an already orthonormal block.  T = R^-1 from the Cholesky factor of G (CholeskyQR) when G is safely positive
+// definite; otherwise the SVQB transform T = D U S^-1/2 (Jacobi on the scaled Gram matrix), which also handles
+// rank-deficient blocks: directions with S below threshold are refilled with pseudo-random vectors, which is
+// what Householder QR effectively returns for them.
 void dav_solver::orthonormalize_block(double* Cblk, int b, int kold, double* dest) {
   const int sp = begin_span(SPAN_ORTH);
   double* cur = Cblk;
@@ -374,20 +376,23 @@ void dav_solver::orthonormalize_block(double* Cblk, int b, int kold, double* des
     gemm(stream, false, nl, b, kold, -1.0, V.p, ldv, G.p, kold, 1.0, cur, ldv, nullptr, 0);
     gemm(stream, true, b, b, nl, 1.0, cur, ldv, cur, ldv, 0.0, S1.p, b, gemm_ws.p, gemm_ws.n);
     allreduce(S1.p, (size_t)b * b);
-    if (pass >= 1) {
-      max_abs_dev(stream, kold, b, G.p, kold, false, small.p);
-      max_abs_dev(stream, b, b, S1.p, b, true, small.p + 1);
-      double h[2];
-      CK(cudaMemcpyAsync(h, small.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
-      CK(cudaStreamSynchronize(stream));
-      // this pass starts from a block that is orthonormal to 1e-6: after it the error is O(eps)
-      if (h[0] < 1e-6 && h[1] < 1e-6) done = true;
+    max_abs_dev(stream, kold, b, G.p, kold, false, small.p);
+    max_abs_dev(stream, b, b, S1.p, b, true, small.p + 1);
+    const bool tried_chol = chol_inv_upper(stream, b, S1.p, Tm.p, small.p + 2);
+    double h[3] = {0.0, 0.0, 1.0};
+    CK(cudaMemcpyAsync(h, small.p, (tried_chol ? 3 : 2) * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    // this pass starts from a block that is orthonormal to 1e-6: after it the error is O(eps)
+    if (pass >= 1 && h[0] < 1e-6 && h[1] < 1e-6) done = true;
+    const bool use_svqb = !tried_chol || h[2] != 0.0;
+    if (use_svqb) {
+      gram_prescale(stream, b, S1.p, D.p);
+      jacobi_eigh(stream, b, S1.p, U.p, sv.p, jscratch.p, status.p);
+      svqb_make_T(stream, b, U.p, sv.p, D.p, Tm.p, flags.p);
+      done = false;  // a rank-deficient / ill-conditioned pass is never the last one
     }
-    gram_prescale(stream, b, S1.p, D.p);
-    jacobi_eigh(stream, b, S1.p, U.p, sv.p, jscratch.p, status.p);
-    svqb_make_T(stream, b, U.p, sv.p, D.p, Tm.p, flags.p);
     gemm(stream, false, nl, b, b, 1.0, cur, ldv, Tm.p, b, 0.0, other, ldv, nullptr, 0);
-    fill_random_cols(stream, other, ldv, nl, row0, flags.p, b, 0x5EEDULL + (uint64_t)pass);
+    if (use_svqb) fill_random_cols(stream, other, ldv, nl, row0, flags.p, b, 0x5EEDULL + (uint64_t)pass);
     std::swap(cur, other);
   }
   if (!done) DAV_THROW(DAV_ERR_NO_CONVERGENCE, "block orthonormalisation did not converge");

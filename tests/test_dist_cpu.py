@@ -1,0 +1,93 @@
+"""world_size-2 gloo tests (CPU) of the host-side logic of the row-block sharded path: the row partition,
+the staged all-gather layout, the bootstrap broadcast and the exchange pattern of one expansion step
+(all-gather of the new block, all-reduce of projection / Gram / norm partials) reproduce the
+single-process numbers."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, n, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fortran_davidson_b200 import dist as fdist
+        from oracle import oracle as orc
+
+        # bootstrap broadcast (what carries the NCCL unique id on the GPU box)
+        payload = fdist.broadcast_bytes(bytes(range(128)) if rank == 0 else None)
+        assert payload == bytes(range(128))
+        assert fdist.max_over_ranks(float(rank), device="cpu") == float(world - 1)
+
+        r0, r1 = fdist.partition_rows(n, world, rank)
+        chunk = fdist.chunk_rows(n, world)
+        spans = [None] * world
+        dist.all_gather_object(spans, (r0, r1))
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        for a, b in zip(spans[:-1], spans[1:]):
+            assert a[1] == b[0] and (a[1] - a[0]) == chunk
+
+        # one expansion step, sharded: A rows, V rows, new block Q rows
+        A = orc.generate_diagonal_dominant(n, 1e-3, None, 5)
+        k, b = 6, 6
+        rng = np.random.default_rng(0)
+        Vfull = np.linalg.qr(rng.standard_normal((n, k)))[0]
+        Cfull = rng.standard_normal((n, b))
+        A_loc, V_loc, C_loc = A[r0:r1], Vfull[r0:r1], Cfull[r0:r1]
+
+        def allreduce(x):
+            t = torch.from_numpy(np.ascontiguousarray(x))
+            dist.all_reduce(t)
+            return t.numpy()
+
+        def allgather_rows(x_loc):
+            send = torch.from_numpy(np.ascontiguousarray(fdist.stage_block(x_loc, chunk)))
+            recv = [torch.empty_like(send) for _ in range(world)]
+            dist.all_gather(recv, send)
+            return fdist.unstage_allgather([t.numpy() for t in recv], n)
+
+        # project out V (partial Gram all-reduced), column norms, all-gather, block matvec, projection
+        G = allreduce(V_loc.T @ C_loc)
+        C_loc = C_loc - V_loc @ G
+        n2 = allreduce((C_loc * C_loc).sum(axis=0))
+        Q_loc = C_loc / np.sqrt(n2)
+        Qfull = allgather_rows(Q_loc)
+        AQ_loc = A_loc @ Qfull
+        P = allreduce(np.hstack([V_loc, Q_loc]).T @ AQ_loc)
+
+        Cref = Cfull - Vfull @ (Vfull.T @ Cfull)
+        Qref = Cref / np.linalg.norm(Cref, axis=0)
+        assert np.allclose(Qfull, Qref, rtol=1e-13, atol=1e-14)
+        Pref = np.hstack([Vfull, Qref]).T @ (A @ Qref)
+        assert np.allclose(P, Pref, rtol=1e-12, atol=1e-12)
+        assert np.allclose(AQ_loc, (A @ Qref)[r0:r1], rtol=1e-12, atol=1e-13)
+        q.put((rank, "ok"))
+    except Exception as ex:  # pragma: no cover
+        q.put((rank, repr(ex)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [300, 1000])
+def test_sharded_exchange_pattern_gloo(n):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + n % 7
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, "ok"), (1, "ok")], results
