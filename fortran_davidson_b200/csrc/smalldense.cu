@@ -204,31 +204,26 @@ __global__ void __launch_bounds__(512) jacobi_sweeps_kernel(int k, const double*
                                                             int* __restrict__ rank_out, double2* __restrict__ rotlog,
                                                             int* __restrict__ nrounds_out, int max_rounds,
                                                             int* status) {
+  // Only the upper triangle of S is kept up to date: element (a, b) lives at [min(a,b) + max(a,b) * ld].  The
+  // round is bound by shared-memory instruction issue, so the per-pair parameters are packed ((c,s) as one
+  // double2, (p,q) as one int2, the work item (iP,iQ) as one 32-bit word) and nothing is mirrored.
   extern __shared__ __align__(16) double sm[];
   const int kp = k + (k & 1), np = kp / 2, ld = kp + 1;
   const int tid = threadIdx.x, nt = blockDim.x;
-  double* red = sm;                                  // 32
-  double* rc = red + 32;                             // np
-  double* rs = rc + np;                              // np
-  double* wv = rs + np;                              // kp
-  int* rp = reinterpret_cast<int*>(wv + kp);         // np
-  int* rq = rp + np;                                 // np
+  double* red = sm;                                         // 32
+  double2* rcs = reinterpret_cast<double2*>(red + 32);      // np  (c, s)
+  double* wv = reinterpret_cast<double*>(rcs + np);         // kp
+  int2* rpq = reinterpret_cast<int2*>(wv + kp);             // np  (p, q)
   const int nitems = np * (np + 1) / 2;
-  unsigned short* itab = reinterpret_cast<unsigned short*>(rq + np);  // 2 * nitems
-  size_t off = 32 + 2 * (size_t)np + kp + ((2 * (size_t)np) * sizeof(int) + 4 * (size_t)nitems + 7) / 8;
+  unsigned* itab = reinterpret_cast<unsigned*>(rpq + np);   // nitems (iP | iQ << 16)
+  size_t off = 32 + 2 * (size_t)np + kp + (size_t)np + ((size_t)nitems * 4 + 7) / 8;
   off = (off + 1) & ~(size_t)1;
   double* S = sm + off;
 
-  // triangular work table: item e -> (iP <= iQ)
   for (int e = tid; e < np * np; e += nt) {
     const int iP = e % np, iQ = e / np;
-    if (iP <= iQ) {
-      const int idx = iQ * (iQ + 1) / 2 + iP;
-      itab[2 * idx] = (unsigned short)iP;
-      itab[2 * idx + 1] = (unsigned short)iQ;
-    }
+    if (iP <= iQ) itab[iQ * (iQ + 1) / 2 + iP] = (unsigned)iP | ((unsigned)iQ << 16);
   }
-  // load, symmetrise from the upper triangle (DSYEV 'U'), find the scale
   double mx = 0.0;
   for (int e = tid; e < kp * kp; e += nt) {
     const int i = e % kp, j = e / kp;
@@ -258,13 +253,14 @@ __global__ void __launch_bounds__(512) jacobi_sweeps_kernel(int k, const double*
   const double abs_thr = EPS * normF / (16.0 * kp);
 
   const int m = kp - 1;
+  // this thread's pair of the current round, advanced incrementally (a, b -> a+1, b+1 mod m)
+  int pa = (tid == 0) ? kp - 1 : tid % m, pb = (tid == 0) ? 0 : (m - (tid % m)) % m;
   int round = 0;
   for (int sweep = 0; sweep < MAX_SWEEPS; ++sweep) {
     int rotated = 0;
     for (int r = 0; r < m; ++r, ++round) {
       if (tid < np) {
-        int p, q;
-        rr_pair(kp, r, tid, p, q);
+        const int p = min(pa, pb), q = max(pa, pb);
         double c = 1.0, s = 0.0;
         if (q < k) {
           const double apq = S[p + q * ld], app = S[p + p * ld], aqq = S[q + q * ld];
@@ -282,34 +278,36 @@ __global__ void __launch_bounds__(512) jacobi_sweeps_kernel(int k, const double*
             rotated = 1;
           }
         }
-        rc[tid] = c; rs[tid] = s; rp[tid] = p; rq[tid] = q;
+        rcs[tid] = make_double2(c, s);
+        rpq[tid] = make_int2(p, q);
         if (round < max_rounds) rotlog[(size_t)round * np + tid] = make_double2(c, s);
+        // next round's pair
+        if (tid == 0) { pb = (pb + 1 == m) ? 0 : pb + 1; }
+        else { pa = (pa + 1 == m) ? 0 : pa + 1; pb = (pb + 1 == m) ? 0 : pb + 1; }
       }
       __syncthreads();
       for (int e = tid; e < nitems; e += nt) {
-        const int iP = itab[2 * e], iQ = itab[2 * e + 1];
-        const double sP = rs[iP], sQ = rs[iQ];
-        if (sP == 0.0 && sQ == 0.0) continue;
-        const double cP = rc[iP], cQ = rc[iQ];
-        const int p1 = rp[iP], q1 = rq[iP], p2 = rp[iQ], q2 = rq[iQ];
+        const unsigned it = itab[e];
+        const int iP = it & 0xffff, iQ = it >> 16;
+        const double2 P = rcs[iP], Q = rcs[iQ];
+        if (P.y == 0.0 && Q.y == 0.0) continue;
+        const int2 pp = rpq[iP], qq = rpq[iQ];
+        const int p1 = pp.x, q1 = pp.y, p2 = qq.x, q2 = qq.y;
         if (iP == iQ) {
           const double apq = S[p1 + q1 * ld], app = S[p1 + p1 * ld], aqq = S[q1 + q1 * ld];
-          const double cc = cP * cP, ss = sP * sP, cs2 = 2.0 * cP * sP;
+          const double cc = P.x * P.x, ss = P.y * P.y, cs2 = 2.0 * P.x * P.y;
           S[p1 + p1 * ld] = cc * app - cs2 * apq + ss * aqq;
           S[q1 + q1 * ld] = ss * app + cs2 * apq + cc * aqq;
-          const double off = cP * sP * (app - aqq) + (cc - ss) * apq;  // ~ eps * |apq|: annihilated up to round-off
-          S[p1 + q1 * ld] = off;
-          S[q1 + p1 * ld] = off;
+          S[p1 + q1 * ld] = P.x * P.y * (app - aqq) + (cc - ss) * apq;  // ~ eps |apq|: annihilated to round-off
         } else {
-          const double m00 = S[p1 + p2 * ld], m01 = S[p1 + q2 * ld], m10 = S[q1 + p2 * ld], m11 = S[q1 + q2 * ld];
-          const double r00 = cP * m00 - sP * m10, r01 = cP * m01 - sP * m11;
-          const double r10 = sP * m00 + cP * m10, r11 = sP * m01 + cP * m11;
-          const double n00 = cQ * r00 - sQ * r01, n01 = sQ * r00 + cQ * r01;
-          const double n10 = cQ * r10 - sQ * r11, n11 = sQ * r10 + cQ * r11;
-          S[p1 + p2 * ld] = n00; S[p2 + p1 * ld] = n00;
-          S[p1 + q2 * ld] = n01; S[q2 + p1 * ld] = n01;
-          S[q1 + p2 * ld] = n10; S[p2 + q1 * ld] = n10;
-          S[q1 + q2 * ld] = n11; S[q2 + q1 * ld] = n11;
+          // upper-triangle addresses of the four elements of the 2x2 block
+          const int a00 = min(p1, p2) + max(p1, p2) * ld, a01 = min(p1, q2) + max(p1, q2) * ld;
+          const int a10 = min(q1, p2) + max(q1, p2) * ld, a11 = min(q1, q2) + max(q1, q2) * ld;
+          const double m00 = S[a00], m01 = S[a01], m10 = S[a10], m11 = S[a11];
+          const double r00 = P.x * m00 - P.y * m10, r01 = P.x * m01 - P.y * m11;
+          const double r10 = P.y * m00 + P.x * m10, r11 = P.y * m01 + P.x * m11;
+          S[a00] = Q.x * r00 - Q.y * r01; S[a01] = Q.y * r00 + Q.x * r01;
+          S[a10] = Q.x * r10 - Q.y * r11; S[a11] = Q.y * r10 + Q.x * r11;
         }
       }
       __syncthreads();
@@ -338,8 +336,9 @@ __global__ void __launch_bounds__(512) jacobi_sweeps_kernel(int k, const double*
 
 // Replays the rotation log on the rows of V = I.  A warp owns 2 rows x 16 lanes per row: the rotations of one
 // round touch disjoint column pairs, so the 16 lanes of a row work independently and only a __syncwarp
-// separates rounds.  CTA = 8 warps = 16 rows.
-constexpr int VROWS = 16, VPARTS = 16;
+// separates rounds.  The log is staged through shared memory in chunks of VCHUNK rounds (coalesced loads, one
+// block barrier per chunk); pair indices advance incrementally (a, b -> a+1, b+1 mod m).  CTA = 8 warps = 16 rows.
+constexpr int VROWS = 16, VPARTS = 16, VCHUNK = 16, VMAXI = 8;  // np <= VPARTS * VMAXI = 128 pairs (k <= 256)
 __global__ void __launch_bounds__(VROWS * VPARTS) jacobi_vectors_kernel(int k, const double2* __restrict__ rotlog,
                                                                       const int* __restrict__ nrounds_in,
                                                                       const int* __restrict__ rank,
@@ -348,25 +347,44 @@ __global__ void __launch_bounds__(VROWS * VPARTS) jacobi_vectors_kernel(int k, c
   const int kp = k + (k & 1), np = kp / 2, ld = kp + 1, m = kp - 1;
   const int lrow = threadIdx.x / VPARTS, part = threadIdx.x % VPARTS;  // lanes 0-15: one row, 16-31: the next
   const int row = blockIdx.x * VROWS + lrow;
-  double* vr = sm + (size_t)lrow * ld;
+  double2* chunk = reinterpret_cast<double2*>(sm);                     // VCHUNK * np
+  double* vr = sm + 2 * (size_t)VCHUNK * np + (size_t)lrow * ld;
   for (int j = part; j < kp; j += VPARTS) vr[j] = (j == row) ? 1.0 : 0.0;
-  __syncwarp();
-  const int nrounds = *nrounds_in;
-  for (int round = 0; round < nrounds; ++round) {
-    const int r = round % m;
-    const double2* rl = rotlog + (size_t)round * np;
-    for (int i = part; i < np; i += VPARTS) {
-      const double2 cs = __ldg(rl + i);
-      if (cs.y != 0.0) {
-        int p, q;
-        rr_pair(kp, r, i, p, q);
-        const double vp = vr[p], vq = vr[q];
-        vr[p] = cs.x * vp - cs.y * vq;
-        vr[q] = cs.y * vp + cs.x * vq;
-      }
-    }
-    __syncwarp();
+  // pairs of round 0 for this lane's pair slots i = part, part + 16, ...
+  int pa[VMAXI], pb[VMAXI];
+#pragma unroll
+  for (int t = 0; t < VMAXI; ++t) {
+    const int i = part + t * VPARTS;
+    if (i == 0) { pa[t] = kp - 1; pb[t] = 0; }
+    else { pa[t] = i % m; pb[t] = (m - (i % m)) % m; }
   }
+  const int nrounds = *nrounds_in;
+  for (int r0 = 0; r0 < nrounds; r0 += VCHUNK) {
+    const int nr = min(VCHUNK, nrounds - r0);
+    __syncthreads();  // previous chunk fully consumed
+    for (int e = threadIdx.x; e < nr * np; e += blockDim.x) chunk[e] = rotlog[(size_t)r0 * np + e];
+    __syncthreads();
+    for (int rr = 0; rr < nr; ++rr) {
+      const double2* rl = chunk + rr * np;
+#pragma unroll
+      for (int t = 0; t < VMAXI; ++t) {
+        const int i = part + t * VPARTS;
+        if (i < np) {
+          const double2 cs = rl[i];
+          if (cs.y != 0.0) {
+            const int p = min(pa[t], pb[t]), q = max(pa[t], pb[t]);
+            const double vp = vr[p], vq = vr[q];
+            vr[p] = cs.x * vp - cs.y * vq;
+            vr[q] = cs.y * vp + cs.x * vq;
+          }
+          if (i == 0) { pb[t] = (pb[t] + 1 == m) ? 0 : pb[t] + 1; }
+          else { pa[t] = (pa[t] + 1 == m) ? 0 : pa[t] + 1; pb[t] = (pb[t] + 1 == m) ? 0 : pb[t] + 1; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  __syncwarp();
   if (row < k)
     for (int j = part; j < k; j += VPARTS) Y[row + (size_t)rank[j] * k] = vr[j];
 }
@@ -556,14 +574,14 @@ void jacobi_eigh(cudaStream_t s, int k, double* S, double* Y, double* w, double*
   // ---- fast path: S in shared memory, rotations logged, V replayed by a second kernel
   {
     const int nitems = np * (np + 1) / 2;
-    size_t small = 32 + 2 * (size_t)np + kp + ((2 * (size_t)np) * sizeof(int) + 4 * (size_t)nitems + 7) / 8;
+    size_t small = 32 + 2 * (size_t)np + kp + (size_t)np + ((size_t)nitems * 4 + 7) / 8;
     small = (small + 1) & ~(size_t)1;
     const size_t need = (small + (size_t)kp * (kp + 1)) * sizeof(double);
     // scratch layout: [rotation log: max_rounds * np double2][rank: k ints][nrounds: 1 int]
     const size_t scratch_doubles = jacobi_scratch_doubles(k);
     const size_t tail = ((size_t)k + 2) / 2 + 2;  // doubles reserved for the int arrays
     const int max_rounds = (int)std::min<size_t>((scratch_doubles - tail) / (2 * (size_t)np), (size_t)MAX_SWEEPS * (kp - 1));
-    if (need <= (size_t)max_smem && max_rounds >= 8 * (kp - 1)) {
+    if (need <= (size_t)max_smem && max_rounds >= 8 * (kp - 1) && np <= VPARTS * VMAXI) {
       double2* rotlog = reinterpret_cast<double2*>(scratch);
       int* rank = reinterpret_cast<int*>(scratch + scratch_doubles - tail);
       int* nrounds = rank + k;
@@ -571,7 +589,7 @@ void jacobi_eigh(cudaStream_t s, int k, double* S, double* Y, double* w, double*
       jacobi_sweeps_kernel<<<1, threads, need, s>>>(k, S, w, rank, rotlog, nrounds, max_rounds, status);
       CK_LAUNCH();
       ++g_kernel_launches;
-      const size_t vsm = (size_t)VROWS * (kp + 1) * sizeof(double);
+      const size_t vsm = (2 * (size_t)VCHUNK * np + (size_t)VROWS * (kp + 1)) * sizeof(double);
       jacobi_vectors_kernel<<<(k + VROWS - 1) / VROWS, VROWS * VPARTS, vsm, s>>>(k, rotlog, nrounds, rank, Y);
       CK_LAUNCH();
       ++g_kernel_launches;
