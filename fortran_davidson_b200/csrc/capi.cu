@@ -350,13 +350,15 @@ int dav_generate_preconditioner(int64_t n, const double* diag, int dim_sub, doub
   API_BEGIN
   need(n >= 1 && diag && precond && dim_sub >= 1 && dim_sub <= n && ld >= n, "bad arguments");
   Ctx c;
-  DevBuf<double> d, val;
-  DevBuf<int64_t> idx;
+  need(dim_sub <= 1024, "generate_preconditioner: dim_sub <= 1024 supported");
+  DevBuf<double> d, val, sv;
+  DevBuf<int64_t> idx, si;
   DevBuf<int> status;
   d.alloc(n); val.alloc(dim_sub); idx.alloc(dim_sub); status.alloc(1);
+  sv.alloc(topk_scratch_entries(n, dim_sub)); si.alloc(topk_scratch_entries(n, dim_sub));
   CK(cudaMemsetAsync(status.p, 0, sizeof(int), c.s));
   h2d(d.p, diag, n, c.s);
-  topk_smallest(c.s, d.p, nullptr, n, 0, dim_sub, val.p, idx.p, status.p);
+  topk_smallest(c.s, d.p, nullptr, n, 0, dim_sub, val.p, idx.p, status.p, sv.p, si.p);
   std::vector<int64_t> hidx(dim_sub);
   CK(cudaMemcpyAsync(hidx.data(), idx.p, (size_t)dim_sub * 8, cudaMemcpyDeviceToHost, c.s));
   check_status_dev(c, status.p, "generate_preconditioner");
@@ -505,21 +507,37 @@ int dav_lapack_sort(char id, int64_t n, double* vector, int32_t* keys) {
   std::vector<double> h(vector, vector + n);
   if (id == 'D')
     for (auto& v : h) v = -v;
-  DevBuf<double> d, val;
-  DevBuf<int64_t> idx;
+  // ranks by selection of the (up to 1024) smallest, repeated on the remainder: the device path used by the
+  // solver (top-2L of the diagonal) generalised to a full ordering
+  DevBuf<double> d, val, sv;
+  DevBuf<int64_t> idx, gi, si;
   DevBuf<int> status;
-  d.alloc(n); val.alloc(n); idx.alloc(n); status.alloc(1);
+  d.alloc(n); gi.alloc(n); status.alloc(1);
+  const int kmax = (int)std::min<int64_t>(n, 1024);
+  val.alloc(kmax); idx.alloc(kmax);
+  sv.alloc(topk_scratch_entries(n, kmax)); si.alloc(topk_scratch_entries(n, kmax));
   CK(cudaMemsetAsync(status.p, 0, sizeof(int), c.s));
-  h2d(d.p, h.data(), n, c.s);
-  topk_smallest(c.s, d.p, nullptr, n, 0, (int)n, val.p, idx.p, status.p);
-  std::vector<int64_t> hidx(n);
-  CK(cudaMemcpyAsync(hidx.data(), idx.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c.s));
-  d2h(h.data(), val.p, n, c.s);
-  check_status_dev(c, status.p, "lapack_sort");
-  for (int64_t t = 0; t < n; ++t) {
-    vector[t] = (id == 'D') ? -h[t] : h[t];
-    keys[hidx[t]] = (int32_t)(t + 1);
+  std::vector<int64_t> hg(n), hidx(kmax);
+  std::vector<double> hv(kmax);
+  for (int64_t t = 0; t < n; ++t) hg[t] = t;
+  std::vector<double> sorted(n);
+  int64_t done = 0;
+  while (done < n) {
+    const int kk = (int)std::min<int64_t>(kmax, n - done);
+    h2d(d.p, h.data(), n, c.s);
+    CK(cudaMemcpyAsync(gi.p, hg.data(), (size_t)n * 8, cudaMemcpyHostToDevice, c.s));
+    topk_smallest(c.s, d.p, gi.p, n, 0, kk, val.p, idx.p, status.p, sv.p, si.p);
+    CK(cudaMemcpyAsync(hidx.data(), idx.p, (size_t)kk * 8, cudaMemcpyDeviceToHost, c.s));
+    d2h(hv.data(), val.p, kk, c.s);
+    check_status_dev(c, status.p, "lapack_sort");
+    for (int t = 0; t < kk; ++t) {
+      sorted[done + t] = hv[t];
+      keys[hidx[t]] = (int32_t)(done + t + 1);
+      hg[hidx[t]] = -1;  // consumed: padding for the next round
+    }
+    done += kk;
   }
+  for (int64_t t = 0; t < n; ++t) vector[t] = (id == 'D') ? -sorted[t] : sorted[t];
   API_END
 }
 

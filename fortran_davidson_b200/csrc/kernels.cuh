@@ -69,10 +69,15 @@ void copy_matrix(cudaStream_t s, int64_t rows, int64_t cols, const double* src, 
 void gen_diag_dominant(cudaStream_t s, double* A, int64_t lda, int64_t nl, int64_t n, int64_t row0, double sparsity,
                        int has_diag, double diag_val, uint64_t seed);
 void extract_diag(cudaStream_t s, const double* A, int64_t lda, int64_t nl, int64_t row0, double* out);
-// (value,index) of the `k` smallest entries of diag[0..nl) (global index = row0 + i), ascending,
-// ties by index.  Single CTA.  status |= 1 on NaN.
+// (value,index) of the `k` smallest entries of diag[0..count) (global index = gidx[i] or row0 + i), ascending,
+// ties by index (entries with a negative gidx are padding).  Multi-CTA rank counting.  status |= 1 on NaN.
+// scratch_val / scratch_idx: >= topk_scratch_entries(count, k) entries each.
+inline size_t topk_scratch_entries(int64_t count, int k) {
+  return 2 * ((size_t)((count + 1023) / 1024) * (size_t)k + (size_t)k);
+}
 void topk_smallest(cudaStream_t s, const double* diag, const int64_t* gidx /*nullable*/, int64_t count,
-                   int64_t row0, int k, double* out_val, int64_t* out_idx, int* status);
+                   int64_t row0, int k, double* out_val, int64_t* out_idx, int* status, double* scratch_val,
+                   int64_t* scratch_idx);
 // V(nl x k) one-hot: V(idx[j]-row0, j) = 1 when idx[j] is a local row
 void set_onehot(cudaStream_t s, double* V, int64_t ldv, int64_t nl, int64_t row0, const int64_t* idx, int k);
 // out(:, j) = A(:, idx[j])   (A is nl x n local row block)

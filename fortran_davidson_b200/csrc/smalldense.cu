@@ -260,10 +260,13 @@ __global__ void __launch_bounds__(512) jacobi_sweeps_kernel(int k, const double*
     int rotated = 0;
     for (int r = 0; r < m; ++r, ++round) {
       if (tid < np) {
-        const int p = min(pa, pb), q = max(pa, pb);
+        // pairs are kept UNSORTED: pa walks up and pb walks down with the pair slot, so a warp's 32 work items
+        // touch 32 consecutive rows -- with ld = 1 (mod 16) element (r, c) sits in bank (r + c) mod 16 whichever
+        // triangle it is read from, i.e. the accesses below are shared-memory bank-conflict free
+        const int p = pa, q = pb;
         double c = 1.0, s = 0.0;
-        if (q < k) {
-          const double apq = S[p + q * ld], app = S[p + p * ld], aqq = S[q + q * ld];
+        if (p < k && q < k) {
+          const double apq = S[min(p, q) + max(p, q) * ld], app = S[p + p * ld], aqq = S[q + q * ld];
           const double aa = fabs(apq);
           if (aa > abs_thr && aa * aa > (EPS * EPS) * fabs(app * aqq)) {
             // t = sign(tau) / (|tau| + sqrt(1 + tau^2)), tau = (aqq - app) / (2 apq), without forming tau;
@@ -294,11 +297,12 @@ __global__ void __launch_bounds__(512) jacobi_sweeps_kernel(int k, const double*
         const int2 pp = rpq[iP], qq = rpq[iQ];
         const int p1 = pp.x, q1 = pp.y, p2 = qq.x, q2 = qq.y;
         if (iP == iQ) {
-          const double apq = S[p1 + q1 * ld], app = S[p1 + p1 * ld], aqq = S[q1 + q1 * ld];
+          const int apq_i = min(p1, q1) + max(p1, q1) * ld;
+          const double apq = S[apq_i], app = S[p1 + p1 * ld], aqq = S[q1 + q1 * ld];
           const double cc = P.x * P.x, ss = P.y * P.y, cs2 = 2.0 * P.x * P.y;
           S[p1 + p1 * ld] = cc * app - cs2 * apq + ss * aqq;
           S[q1 + q1 * ld] = ss * app + cs2 * apq + cc * aqq;
-          S[p1 + q1 * ld] = P.x * P.y * (app - aqq) + (cc - ss) * apq;  // ~ eps |apq|: annihilated to round-off
+          S[apq_i] = P.x * P.y * (app - aqq) + (cc - ss) * apq;  // ~ eps |apq|: annihilated to round-off
         } else {
           // upper-triangle addresses of the four elements of the 2x2 block
           const int a00 = min(p1, p2) + max(p1, p2) * ld, a01 = min(p1, q2) + max(p1, q2) * ld;
@@ -372,7 +376,7 @@ __global__ void __launch_bounds__(VROWS * VPARTS) jacobi_vectors_kernel(int k, c
         if (i < np) {
           const double2 cs = rl[i];
           if (cs.y != 0.0) {
-            const int p = min(pa[t], pb[t]), q = max(pa[t], pb[t]);
+            const int p = pa[t], q = pb[t];
             const double vp = vr[p], vq = vr[q];
             vr[p] = cs.x * vp - cs.y * vq;
             vr[q] = cs.y * vp + cs.x * vq;

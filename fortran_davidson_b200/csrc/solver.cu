@@ -292,6 +292,12 @@ void dav_solver::alloc_work(int lowest, int kcap_) {
   idx.alloc(2 * (size_t)lowest);
   cand_val.alloc((size_t)2 * lowest * std::max(1, comm.world()) + 2 * (size_t)lowest);
   cand_idx.alloc((size_t)2 * lowest * std::max(1, comm.world()) + 2 * (size_t)lowest);
+  {
+    const size_t e = std::max(topk_scratch_entries(nl, 2 * lowest),
+                              topk_scratch_entries((int64_t)2 * lowest * std::max(1, comm.world()), 2 * lowest));
+    topk_val.alloc(e);
+    topk_idx.alloc(e);
+  }
   // everything the loop touches is allocated up front: no cudaMalloc inside the iteration
   const int bmax = std::max(2 * lowest, kcap / 2);
   const bool any_free = mat[0].kind != DENSE || (mat[1].kind != NONE && mat[1].kind != DENSE);
@@ -431,14 +437,15 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
   int sp = begin_span(SPAN_INIT);
   ensure_diag(0);
   if (gev) ensure_diag(1);
-  topk_smallest(stream, mat[0].diag.p, nullptr, nl, row0, k0, cand_val.p, cand_idx.p, status.p);
+  topk_smallest(stream, mat[0].diag.p, nullptr, nl, row0, k0, cand_val.p, cand_idx.p, status.p, topk_val.p,
+                topk_idx.p);
   if (comm.active()) {
     const int P = comm.world();
     double* allv = cand_val.p + k0;
     int64_t* alli = cand_idx.p + k0;
     comm.allgather(cand_val.p, allv, (size_t)k0 * 8, stream);
     comm.allgather(cand_idx.p, alli, (size_t)k0 * 8, stream);
-    topk_smallest(stream, allv, alli, (int64_t)k0 * P, 0, k0, cand_val.p, idx.p, status.p);
+    topk_smallest(stream, allv, alli, (int64_t)k0 * P, 0, k0, cand_val.p, idx.p, status.p, topk_val.p, topk_idx.p);
   } else {
     CK(cudaMemcpyAsync(idx.p, cand_idx.p, (size_t)k0 * 8, cudaMemcpyDeviceToDevice, stream));
   }

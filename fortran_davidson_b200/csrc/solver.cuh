@@ -37,8 +37,8 @@ struct dav_solver {
   dav::DevBuf<double> Ap, Bp, Y, theta, G, U, sv, D, Tm, S1, S2, Z, jscratch, norms2, partial, gemm_ws, small;
   dav::DevBuf<int> status, flags, gjd_active;
   dav::DevBuf<double> gjd_buf, gjd_st;
-  dav::DevBuf<int64_t> idx, cand_idx;
-  dav::DevBuf<double> cand_val;
+  dav::DevBuf<int64_t> idx, cand_idx, topk_idx;
+  dav::DevBuf<double> cand_val, topk_val;
   std::vector<double> host_x, host_y;  // callback staging
   std::vector<cudaEvent_t> ev_pool;
   struct Span { int a, b, kind; };

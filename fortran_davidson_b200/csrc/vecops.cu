@@ -47,58 +47,46 @@ __global__ void extract_diag_kernel(const double* __restrict__ A, int64_t lda, i
     out[i] = A[i + (row0 + i) * lda];
 }
 
-// k smallest (value, global index) pairs in ascending lexicographic order: pass t finds the
-// smallest pair strictly greater than the pair picked by pass t-1.  One CTA.
-__global__ void __launch_bounds__(1024) topk_smallest_kernel(const double* __restrict__ diag,
-                                                             const int64_t* __restrict__ gidx, int64_t count,
-                                                             int64_t row0, int k, double* out_val, int64_t* out_idx,
-                                                             int* status) {
-  __shared__ double sval[32];
-  __shared__ long long sidx[32];
-  __shared__ double last_val;
-  __shared__ long long last_idx;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  if (threadIdx.x == 0) { last_val = -INFINITY; last_idx = -1; }
-  __syncthreads();
-  for (int t = 0; t < k; ++t) {
-    const double lv = last_val;
-    const long long li = last_idx;
-    double bv = INFINITY;
-    long long bi = 0x7fffffffffffffffLL;
-    for (int64_t e = threadIdx.x; e < count; e += blockDim.x) {
-      const double v = diag[e];
-      const long long g = gidx ? (long long)gidx[e] : (long long)(row0 + e);
-      if (!(v == v)) atomicOr(status, 1);
-      const bool after = (v > lv) || (v == lv && g > li);
-      const bool better = (v < bv) || (v == bv && g < bi);
-      if (after && better) { bv = v; bi = g; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-    }
-    if (lane == 0) { sval[wid] = bv; sidx[wid] = bi; }
-    __syncthreads();
-    if (wid == 0) {
-      bv = lane < nw ? sval[lane] : INFINITY;
-      bi = lane < nw ? sidx[lane] : 0x7fffffffffffffffLL;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-      }
-      if (lane == 0) {
-        out_val[t] = bv;
-        out_idx[t] = (bi == 0x7fffffffffffffffLL) ? -1 : bi;
-        last_val = bv;
-        last_idx = bi;
-      }
-    }
-    __syncthreads();
+// k smallest (value, global index) pairs in ascending lexicographic order by rank counting: every CTA takes a
+// chunk of 1024 candidates into shared memory, each thread counts how many keys of the chunk precede its own and
+// the keys with rank < k are written at their rank.  Applied repeatedly (chunk winners become the next round's
+// candidates) until one chunk is left; ties are broken by index, so the selection is the stable order.
+constexpr int TOPK_CHUNK = 1024;
+constexpr long long TOPK_PAD = 0x7fffffffffffffffLL;
+__global__ void __launch_bounds__(TOPK_CHUNK) rank_select_kernel(const double* __restrict__ val,
+                                                                 const int64_t* __restrict__ gidx, int64_t count,
+                                                                 int64_t row0, int k, double* __restrict__ out_val,
+                                                                 int64_t* __restrict__ out_idx, int final_round,
+                                                                 int* status) {
+  __shared__ double sv[TOPK_CHUNK];
+  __shared__ long long sg[TOPK_CHUNK];
+  const int t = threadIdx.x;
+  const int64_t e = (int64_t)blockIdx.x * TOPK_CHUNK + t;
+  double v = INFINITY;
+  long long g = TOPK_PAD;
+  if (e < count) {
+    v = val[e];
+    g = gidx ? (long long)gidx[e] : (long long)(row0 + e);
+    if (g < 0) { g = TOPK_PAD; v = INFINITY; }
+    if (!(v == v)) { atomicOr(status, 1); v = INFINITY; }
   }
+  sv[t] = v;
+  sg[t] = g;
+  // empty output slots (fewer than k candidates in this chunk)
+  if (t < k) { out_val[(size_t)blockIdx.x * k + t] = INFINITY; out_idx[(size_t)blockIdx.x * k + t] = -1; }
+  __syncthreads();
+  if (g == TOPK_PAD) return;
+  int rank = 0;
+#pragma unroll 8
+  for (int j = 0; j < TOPK_CHUNK; ++j) {
+    const double vj = sv[j];
+    rank += (vj < v) || (vj == v && sg[j] < g);
+  }
+  if (rank < k) {
+    out_val[(size_t)blockIdx.x * k + rank] = v;
+    out_idx[(size_t)blockIdx.x * k + rank] = (int64_t)g;
+  }
+  (void)final_round;
 }
 
 __global__ void set_onehot_kernel(double* V, int64_t ldv, int64_t nl, int64_t row0, const int64_t* idx, int k) {
@@ -267,9 +255,24 @@ void extract_diag(cudaStream_t s, const double* A, int64_t lda, int64_t nl, int6
 }
 
 void topk_smallest(cudaStream_t s, const double* diag, const int64_t* gidx, int64_t count, int64_t row0, int k,
-                   double* out_val, int64_t* out_idx, int* status) {
-  topk_smallest_kernel<<<1, 1024, 0, s>>>(diag, gidx, count, row0, k, out_val, out_idx, status);
-  LAUNCHED();
+                   double* out_val, int64_t* out_idx, int* status, double* scratch_val, int64_t* scratch_idx) {
+  if (k > TOPK_CHUNK) DAV_THROW(DAV_ERR_INVALID, "top-k selection supports k <= %d", TOPK_CHUNK);
+  // rounds ping-pong between the two halves of the scratch arrays; the last round writes the outputs
+  const size_t half = topk_scratch_entries(count, k) / 2;
+  const double* cv = diag;
+  const int64_t* ci = gidx;
+  int64_t m = count, r0 = row0;
+  int side = 0;
+  for (;;) {
+    const int64_t nch = std::max<int64_t>(1, ceil_div(m, TOPK_CHUNK));
+    double* ov = (nch == 1) ? out_val : scratch_val + side * half;
+    int64_t* oi = (nch == 1) ? out_idx : scratch_idx + side * half;
+    rank_select_kernel<<<(unsigned)nch, TOPK_CHUNK, 0, s>>>(cv, ci, m, r0, k, ov, oi, nch == 1, status);
+    LAUNCHED();
+    if (nch == 1) break;
+    cv = ov; ci = oi; m = nch * k; r0 = 0;
+    side ^= 1;
+  }
 }
 
 void set_onehot(cudaStream_t s, double* V, int64_t ldv, int64_t nl, int64_t row0, const int64_t* idx, int k) {
