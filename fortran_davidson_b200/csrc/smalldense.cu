@@ -289,56 +289,29 @@ __global__ void __launch_bounds__(512) jacobi_sweeps_kernel(int k, const double*
         else { pa = (pa + 1 == m) ? 0 : pa + 1; pb = (pb + 1 == m) ? 0 : pb + 1; }
       }
       __syncthreads();
-      // work items of this thread in batches of IB: gather every operand first, then compute and scatter (the
-      // items of a round touch disjoint elements, which the compiler cannot know -- batching by hand lets the
-      // shared-memory loads of the whole batch overlap)
-      constexpr int IB = 4;
-      for (int e0 = tid; e0 < nitems; e0 += IB * nt) {
-        double2 P[IB], Q[IB];
-        int a00[IB], a01[IB], a10[IB], a11[IB];
-        double m00[IB], m01[IB], m10[IB], m11[IB];
-        bool act[IB], dg[IB];
-#pragma unroll
-        for (int u = 0; u < IB; ++u) {
-          const int e = e0 + u * nt;
-          act[u] = false;
-          dg[u] = false;
-          if (e < nitems) {
-            const unsigned it = itab[e];
-            const int iP = it & 0xffff, iQ = it >> 16;
-            P[u] = rcs[iP];
-            Q[u] = rcs[iQ];
-            if (P[u].y != 0.0 || Q[u].y != 0.0) {
-              act[u] = true;
-              dg[u] = (iP == iQ);
-              const int2 pp = rpq[iP], qq = rpq[iQ];
-              const int p1 = pp.x, q1 = pp.y, p2 = qq.x, q2 = qq.y;
-              if (dg[u]) {
-                a00[u] = p1 + p1 * ld; a11[u] = q1 + q1 * ld;
-                a01[u] = min(p1, q1) + max(p1, q1) * ld; a10[u] = a01[u];
-              } else {
-                a00[u] = min(p1, p2) + max(p1, p2) * ld; a01[u] = min(p1, q2) + max(p1, q2) * ld;
-                a10[u] = min(q1, p2) + max(q1, p2) * ld; a11[u] = min(q1, q2) + max(q1, q2) * ld;
-              }
-              m00[u] = S[a00[u]]; m01[u] = S[a01[u]]; m10[u] = S[a10[u]]; m11[u] = S[a11[u]];
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < IB; ++u) {
-          if (!act[u]) continue;
-          if (dg[u]) {
-            const double app = m00[u], aqq = m11[u], apq = m01[u];
-            const double cc = P[u].x * P[u].x, ss = P[u].y * P[u].y, cs2 = 2.0 * P[u].x * P[u].y;
-            S[a00[u]] = cc * app - cs2 * apq + ss * aqq;
-            S[a11[u]] = ss * app + cs2 * apq + cc * aqq;
-            S[a01[u]] = P[u].x * P[u].y * (app - aqq) + (cc - ss) * apq;  // ~ eps |apq|: annihilated to round-off
-          } else {
-            const double r00 = P[u].x * m00[u] - P[u].y * m10[u], r01 = P[u].x * m01[u] - P[u].y * m11[u];
-            const double r10 = P[u].y * m00[u] + P[u].x * m10[u], r11 = P[u].y * m01[u] + P[u].x * m11[u];
-            S[a00[u]] = Q[u].x * r00 - Q[u].y * r01; S[a01[u]] = Q[u].y * r00 + Q[u].x * r01;
-            S[a10[u]] = Q[u].x * r10 - Q[u].y * r11; S[a11[u]] = Q[u].y * r10 + Q[u].x * r11;
-          }
+      for (int e = tid; e < nitems; e += nt) {
+        const unsigned it = itab[e];
+        const int iP = it & 0xffff, iQ = it >> 16;
+        const double2 P = rcs[iP], Q = rcs[iQ];
+        if (P.y == 0.0 && Q.y == 0.0) continue;
+        const int2 pp = rpq[iP], qq = rpq[iQ];
+        const int p1 = pp.x, q1 = pp.y, p2 = qq.x, q2 = qq.y;
+        if (iP == iQ) {
+          const int apq_i = min(p1, q1) + max(p1, q1) * ld;
+          const double apq = S[apq_i], app = S[p1 + p1 * ld], aqq = S[q1 + q1 * ld];
+          const double cc = P.x * P.x, ss = P.y * P.y, cs2 = 2.0 * P.x * P.y;
+          S[p1 + p1 * ld] = cc * app - cs2 * apq + ss * aqq;
+          S[q1 + q1 * ld] = ss * app + cs2 * apq + cc * aqq;
+          S[apq_i] = P.x * P.y * (app - aqq) + (cc - ss) * apq;  // ~ eps |apq|: annihilated to round-off
+        } else {
+          // upper-triangle addresses of the four elements of the 2x2 block
+          const int a00 = min(p1, p2) + max(p1, p2) * ld, a01 = min(p1, q2) + max(p1, q2) * ld;
+          const int a10 = min(q1, p2) + max(q1, p2) * ld, a11 = min(q1, q2) + max(q1, q2) * ld;
+          const double m00 = S[a00], m01 = S[a01], m10 = S[a10], m11 = S[a11];
+          const double r00 = P.x * m00 - P.y * m10, r01 = P.x * m01 - P.y * m11;
+          const double r10 = P.y * m00 + P.x * m10, r11 = P.y * m01 + P.x * m11;
+          S[a00] = Q.x * r00 - Q.y * r01; S[a01] = Q.y * r00 + Q.x * r01;
+          S[a10] = Q.x * r10 - Q.y * r11; S[a11] = Q.y * r10 + Q.x * r11;
         }
       }
       __syncthreads();

@@ -26,11 +26,10 @@ def main():
              (1000, 1e-2, 3, 10, 1e-10, True, "DPR"), (3000, 5e-2, 10, 100, 1e-8, False, "DPR"),
              (700, 1e-2, 3, 10, 1e-9, True, "GJD"), (5000, 1e-3, 8, None, 1e-8, True, "DPR")]
     for (n, sp, L, md, tol, gev, method) in cases:
+        s.clear(1)
         s.generate_diagonal_dominant(0, n, sp, None, 0)
         if gev:
             s.generate_diagonal_dominant(1, n, sp, 1.0, 1)
-        else:
-            s.clear(1)
         ev, vec, iters = s.solve(L, method, 200, tol, md)
         A = orc.generate_diagonal_dominant(n, sp, None, 0)
         B = orc.generate_diagonal_dominant(n, sp, 1.0, 1) if gev else None
