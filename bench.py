@@ -353,8 +353,8 @@ def run_e2e(args, solver, fd, torch, dist, distributed, rank, world, n, L, md, b
                 vec_.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(n), C.byref(it_)))
             ev = ev_
         else:
-            # sharded: every rank uploads its own row block (host pointer offset so that row r0 is its first row)
-            solver.upload_ptr(0, n, ptr - 8 * r0, nl)
+            # sharded: every rank uploads its own row block from its own page-locked host copy
+            solver.upload_rows_ptr(0, n, ptr, nl)
             ev, _v, _it = solver.solve(L, "DPR", 1000, args.tol, md, want_vectors=True)
             solver.clear(0)
         barrier()
@@ -366,7 +366,7 @@ def run_e2e(args, solver, fd, torch, dist, distributed, rank, world, n, L, md, b
     return {"value": t, "unit": UNIT, "h2d_bytes_per_step": int(8 * nl * n * world),
             "d2h_bytes_per_step": int(8 * n * L + 8 * L), "steps": steps,
             "api": "dav_generalized_eigensolver_dense (host pointers, pinned)" if world == 1 else
-                   "dav_matrix_upload + dav_solve per rank (host row blocks, pinned)",
+                   "dav_matrix_upload_rows + dav_solve per rank (host row blocks, pinned)",
             "eigenvalue0": float(ev[0]), "host_memory": "page-locked" if pinned else "pageable", "note": note}
 
 

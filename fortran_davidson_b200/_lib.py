@@ -16,7 +16,8 @@ SYMBOLS = [
     "dav_last_error", "dav_version", "dav_device_count", "dav_generalized_eigensolver_dense",
     "dav_generalized_eigensolver_free", "dav_generalized_eigensolver_free_builtin", "dav_get_unique_id",
     "dav_create", "dav_create_distributed", "dav_destroy", "dav_partition_rows",
-    "dav_matrix_generate_diagonal_dominant", "dav_matrix_upload", "dav_matrix_set_operator",
+    "dav_matrix_generate_diagonal_dominant", "dav_matrix_upload", "dav_matrix_upload_rows",
+    "dav_matrix_set_operator",
     "dav_matrix_set_callback", "dav_matrix_clear", "dav_matrix_download", "dav_solve", "dav_get_stats",
     "dav_set_matvec_impl", "dav_block_matvec", "dav_bench_block_matvec", "dav_generate_diagonal_dominant",
     "dav_generate_preconditioner", "dav_norm", "dav_lapack_generalized_eigensolver",

@@ -182,6 +182,13 @@ int dav_matrix_upload(dav_solver_t* h, int which, int64_t n, const double* host_
   API_END
 }
 
+int dav_matrix_upload_rows(dav_solver_t* h, int which, int64_t n, const double* host_rows, int64_t ld) {
+  API_BEGIN
+  need(h && (which == 0 || which == 1), "bad handle / slot");
+  h->upload_rows(which, n, host_rows, ld);
+  API_END
+}
+
 int dav_matrix_set_operator(dav_solver_t* h, int which, int64_t n, int op) {
   API_BEGIN
   need(h && (which == 0 || which == 1), "bad handle / slot");

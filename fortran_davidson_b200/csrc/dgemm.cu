@@ -116,12 +116,23 @@ __global__ void __launch_bounds__(NT) gemm_kernel(int64_t M, int64_t N, int64_t 
   }
 }
 
-__global__ void splitk_reduce_kernel(int64_t M, int64_t N, int splits, double alpha, const double* __restrict__ ws,
-                                     double beta, double* __restrict__ C, int64_t ldc) {
+// Sums the split-K partials in a fixed order (bit-reproducible).  A CTA owns 64 consecutive output elements; its 4
+// thread groups each add every 4th partial (coalesced 512-byte rows of the workspace) and the 4 group sums are
+// combined in shared memory in group order.
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(int64_t M, int64_t N, int splits, double alpha,
+                                                            const double* __restrict__ ws, double beta,
+                                                            double* __restrict__ C, int64_t ldc) {
+  __shared__ double part[4][64];
   const int64_t total = M * N;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    double s = 0.0;
-    for (int z = 0; z < splits; ++z) s += ws[(size_t)z * total + e];
+  const int el = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int64_t e = (int64_t)blockIdx.x * 64 + el;
+  double s = 0.0;
+  if (e < total)
+    for (int z = g; z < splits; z += 4) s += ws[(size_t)z * total + e];
+  part[g][el] = s;
+  __syncthreads();
+  if (g == 0 && e < total) {
+    s = ((part[0][el] + part[1][el]) + part[2][el]) + part[3][el];
     const int64_t m = e % M, j = e / M;
     double* c = C + m + j * ldc;
     *c = (beta == 0.0) ? alpha * s : alpha * s + beta * (*c);
@@ -136,7 +147,8 @@ void gemm(cudaStream_t s, bool transA, int64_t M, int64_t N, int64_t K, double a
   const int64_t gx = ceil_div(M, BM), gy = ceil_div(N, BN);
   int splits = 1;
   if (K > 1024 && gx * gy < 592) {  // long reduction, few output tiles: split K over the grid
-    splits = (int)std::min<int64_t>(ceil_div(592, gx * gy), ceil_div(K, 256));
+    // about two CTAs per SM in total: more partials only lengthen the reduction (each is M x N doubles of traffic)
+    splits = (int)std::min<int64_t>(ceil_div(296, gx * gy), ceil_div(K, 256));
     const size_t need = (size_t)M * (size_t)N;
     if (ws == nullptr || need == 0) splits = 1;
     else splits = (int)std::min<size_t>((size_t)splits, ws_doubles / need);
@@ -154,7 +166,7 @@ void gemm(cudaStream_t s, bool transA, int64_t M, int64_t N, int64_t K, double a
   ++g_kernel_launches;
   if (splits > 1) {
     const int64_t total = M * N;
-    const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 1184);
+    const int blocks = (int)ceil_div(total, 64);
     splitk_reduce_kernel<<<blocks, 256, 0, s>>>(M, N, splits, alpha, ws, beta, C, ldc);
     CK_LAUNCH();
     ++g_kernel_launches;

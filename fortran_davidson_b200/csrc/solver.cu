@@ -114,6 +114,22 @@ void dav_solver::upload(int which, int64_t n_, const double* host, int64_t ld) {
   m.n = n;
 }
 
+void dav_solver::upload_rows(int which, int64_t n_, const double* host_rows, int64_t ld) {
+  CK(cudaSetDevice(device));
+  clear_matrix(which);
+  set_dims(n_);
+  if (!host_rows || ld < nl) DAV_THROW(DAV_ERR_INVALID, "upload_rows: bad host row block / leading dimension");
+  Matrix& m = mat[which];
+  m.lda = round_up(std::max<int64_t>(nl, 1), 16);
+  m.A.alloc((size_t)m.lda * n);
+  if (nl > 0)
+    CK(cudaMemcpy2DAsync(m.A.p, (size_t)m.lda * 8, host_rows, (size_t)ld * 8, (size_t)nl * 8, (size_t)n,
+                         cudaMemcpyHostToDevice, stream));
+  CK(cudaStreamSynchronize(stream));
+  m.kind = DENSE;
+  m.n = n;
+}
+
 void dav_solver::set_operator(int which, int64_t n_, int op) {
   CK(cudaSetDevice(device));
   if (op < DAV_OP_BENCHMARK_MTX || op > DAV_OP_TEST_STX) DAV_THROW(DAV_ERR_INVALID, "unknown built-in operator %d", op);

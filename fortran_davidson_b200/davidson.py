@@ -146,6 +146,11 @@ class DavidsonSolver:
         check(lib().dav_matrix_upload(self._h, C.c_int(which), C.c_int64(n), C.c_void_p(ptr), C.c_int64(ld)))
         self.n = n
 
+    def upload_rows_ptr(self, which, n, ptr, ld):
+        """This rank's row block only: (rows() x n) column-major host memory at `ptr`, leading dimension ld."""
+        check(lib().dav_matrix_upload_rows(self._h, C.c_int(which), C.c_int64(n), C.c_void_p(ptr), C.c_int64(ld)))
+        self.n = n
+
     def set_operator(self, which, n, op):
         check(lib().dav_matrix_set_operator(self._h, C.c_int(which), C.c_int64(n), C.c_int(op)))
         self.n = n

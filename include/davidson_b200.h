@@ -124,6 +124,9 @@ int dav_matrix_generate_diagonal_dominant(dav_solver_t* h, int which, int64_t n,
                                           double diag_val, uint64_t seed);
 /* upload a host matrix (each rank copies its own row block) */
 int dav_matrix_upload(dav_solver_t* h, int which, int64_t n, const double* host_matrix, int64_t ld);
+/* upload only this rank's row block: host_rows is (row_end-row_begin) x n column-major with leading dimension
+ * ld >= row_end-row_begin (dav_partition_rows); a rank then never needs the whole matrix in host memory */
+int dav_matrix_upload_rows(dav_solver_t* h, int which, int64_t n, const double* host_rows, int64_t ld);
 /* matrix-free: built-in generator or host callback (diag may be NULL) */
 int dav_matrix_set_operator(dav_solver_t* h, int which, int64_t n, int op);
 int dav_matrix_set_callback(dav_solver_t* h, int which, int64_t n, dav_gemv_fn fn, void* ctx, const double* diag);

@@ -19,12 +19,15 @@ def main():
         a = agg.setdefault(row["Kernel Name"].split("(")[0][-70:], [0, 0.0])
         a[0] += 1
         a[1] += v
-    own = sum(t for k, (n, t) in agg.items() if "dav::" in k)
+    def is_own(k):  # ncu prints the anonymous namespace as dav::<unnamed>:: or (application replay) as unnamed>::
+        return "dav::" in k or "unnamed>::" in k
+
+    own = sum(t for k, (n, t) in agg.items() if is_own(k))
     for c in sys.argv[2:]:
         print("# " + c)
     print("# own kernels (dav::) total %.1f us; shares are of that total" % own)
     for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
-        share = "%5.1f%%" % (100 * t / own) if "dav::" in k else "   n/a"
+        share = "%5.1f%%" % (100 * t / own) if is_own(k) else "   n/a"
         print("%-70s n=%4d total_us=%10.1f avg_us=%9.1f share=%s" % (k, n, t, t / n, share))
 
 

@@ -244,6 +244,23 @@ def test_dense_device_generated_matches_uploaded():
     s.close()
 
 
+def test_upload_rows_matches_upload():
+    """dav_matrix_upload_rows (a rank's own row block, its own leading dimension) == dav_matrix_upload."""
+    n = 700
+    A = orc.generate_diagonal_dominant(n, 1e-2, None, 5)
+    s = fd.DavidsonSolver()
+    r0, r1 = 0, n
+    blk = np.zeros((r1 - r0 + 5, n), order="F")  # ld = rows + 5
+    blk[:r1 - r0] = A[r0:r1]
+    s.upload_rows_ptr(0, n, blk.ctypes.data, blk.shape[0])
+    assert np.array_equal(s.download(0), A)
+    ev, vec, iters = s.solve(3, "DPR", 200, 1e-9)
+    s.upload(0, A)
+    ev2, vec2, iters2 = s.solve(3, "DPR", 200, 1e-9)
+    assert iters == iters2 and np.array_equal(ev, ev2) and np.array_equal(vec, vec2)
+    s.close()
+
+
 def test_not_converged_semantics(golden_cases):
     g = golden_cases["notconverged_DPR"]
     A, _ = case_inputs("notconverged_DPR")
