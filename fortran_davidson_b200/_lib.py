@@ -21,7 +21,7 @@ SYMBOLS = [
     "dav_matrix_set_callback", "dav_matrix_clear", "dav_matrix_download", "dav_solve", "dav_get_stats",
     "dav_set_matvec_impl", "dav_block_matvec", "dav_bench_block_matvec", "dav_generate_diagonal_dominant",
     "dav_generate_preconditioner", "dav_norm", "dav_lapack_generalized_eigensolver",
-    "dav_lapack_generalized_eigensolver_lowest", "dav_lapack_qr", "dav_lapack_solver", "dav_lapack_matmul",
+    "dav_lapack_generalized_eigensolver_lowest", "dav_sym_eigh_info", "dav_lapack_qr", "dav_lapack_solver", "dav_lapack_matmul",
     "dav_lapack_matrix_vector", "dav_lapack_sort", "dav_free_matmul", "dav_compute_on_the_fly",
 ]
 

@@ -83,20 +83,20 @@ void eigensolve_dev(Ctx& c, int k, const double* mtx_h, const double* stx_h, dou
   const size_t kk = (size_t)k * k;
   DevBuf<double> S1, S2, U, sv, Tm, Z, Y, w, scratch;
   DevBuf<int> status;
-  S1.alloc(kk); Y.alloc(kk); w.alloc(k); scratch.alloc(jacobi_scratch_doubles(k)); status.alloc(1);
+  S1.alloc(kk); Y.alloc(kk); w.alloc(k); scratch.alloc(sym_eigh_scratch_doubles(k)); status.alloc(1);
   CK(cudaMemsetAsync(status.p, 0, sizeof(int), c.s));
   h2d(S1.p, mtx_h, kk, c.s);
   if (!stx_h) {
-    jacobi_eigh(c.s, k, S1.p, Y.p, w.p, scratch.p, status.p);
+    sym_eigh(c.s, k, S1.p, Y.p, w.p, scratch.p, status.p);
   } else {
     S2.alloc(kk); U.alloc(kk); sv.alloc(k); Tm.alloc(kk); Z.alloc(kk);
     h2d(S2.p, stx_h, kk, c.s);
-    jacobi_eigh(c.s, k, S2.p, U.p, sv.p, scratch.p, status.p);
+    sym_eigh(c.s, k, S2.p, U.p, sv.p, scratch.p, status.p);
     scale_cols_rsqrt_checked(c.s, k, U.p, sv.p, Tm.p, status.p);
     symmetrize_from_upper(c.s, k, S1.p, k);
     gemm(c.s, false, k, k, k, 1.0, S1.p, k, Tm.p, k, 0.0, Z.p, k, nullptr, 0);
     gemm(c.s, true, k, k, k, 1.0, Tm.p, k, Z.p, k, 0.0, S1.p, k, nullptr, 0);
-    jacobi_eigh(c.s, k, S1.p, Z.p, w.p, scratch.p, status.p);
+    sym_eigh(c.s, k, S1.p, Z.p, w.p, scratch.p, status.p);
     gemm(c.s, false, k, k, k, 1.0, Tm.p, k, Z.p, k, 0.0, Y.p, k, nullptr, 0);
   }
   check_status_dev(c, status.p, "lapack_generalized_eigensolver");
@@ -397,6 +397,46 @@ int dav_lapack_generalized_eigensolver(int dim, const double* mtx, const double*
   need(dim >= 1 && mtx && eigenvalues && eigenvectors, "bad arguments");
   Ctx c;
   eigensolve_dev(c, dim, mtx, stx, eigenvalues, eigenvectors, dim);
+  API_END
+}
+
+int dav_sym_eigh_info(int dim, const double* mtx, double* eigenvalues, double* eigenvectors, double* info, int reps,
+                      float* ms_out) {
+  API_BEGIN
+  need(dim >= 1 && mtx && eigenvalues && eigenvectors && info && reps >= 0 && (reps == 0 || ms_out), "bad arguments");
+  Ctx c;
+  const int k = dim;
+  const size_t kk = (size_t)k * k;
+  DevBuf<double> S1, Y, w, scratch;
+  DevBuf<int> status;
+  S1.alloc(kk); Y.alloc(kk); w.alloc(k); scratch.alloc(sym_eigh_scratch_doubles(k)); status.alloc(1);
+  CK(cudaMemsetAsync(status.p, 0, sizeof(int), c.s));
+  h2d(S1.p, mtx, kk, c.s);
+  std::vector<cudaEvent_t> ev(reps + 1);
+  for (auto& e : ev) CK(cudaEventCreate(&e));
+  sym_eigh(c.s, k, S1.p, Y.p, w.p, scratch.p, status.p);
+  for (int r = 0; r < reps; ++r) {
+    CK(cudaEventRecord(ev[r], c.s));
+    sym_eigh(c.s, k, S1.p, Y.p, w.p, scratch.p, status.p);
+  }
+  CK(cudaEventRecord(ev[reps], c.s));
+  check_status_dev(c, status.p, "sym_eigh");
+  for (int r = 0; r < reps; ++r) CK(cudaEventElapsedTime(&ms_out[r], ev[r], ev[r + 1]));
+  for (auto& e : ev) cudaEventDestroy(e);
+  d2h(eigenvalues, w.p, k, c.s);
+  d2h(eigenvectors, Y.p, kk, c.s);
+  for (int q = 0; q < 8; ++q) info[q] = 0.0;
+  info[0] = -1.0;
+  if (sym_eigh_uses_tridiag(k)) {
+    double f[9];
+    CK(cudaMemcpyAsync(f, sym_eigh_flags(scratch.p, k), sizeof(f), cudaMemcpyDeviceToHost, c.s));
+    c.sync();
+    int acc = 0;
+    std::memcpy(&acc, &f[8], sizeof(int));
+    info[0] = acc; info[1] = f[0]; info[2] = f[1]; info[3] = f[2];
+    for (int q = 0; q < 4; ++q) info[4 + q] = f[3 + q];
+  }
+  c.sync();
   API_END
 }
 

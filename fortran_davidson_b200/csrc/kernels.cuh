@@ -40,7 +40,18 @@ void free_column_builtin(cudaStream_t s, int op, int64_t n, int64_t col /*0-base
 // (1 = no convergence / NaN).  scratch: >= jacobi_scratch_doubles(k) doubles of global memory (rotation log of up
 // to 40 sweeps, or the S/V copies of the large-k path).
 inline size_t jacobi_scratch_doubles(int k) { return 44 * (size_t)(k + 2) * (size_t)(k + 2); }
-void jacobi_eigh(cudaStream_t s, int k, double* S, double* Y, double* w, double* scratch, int* status);
+// skip (nullable): device flag; when *skip != 0 at kernel start the call is a no-op (see sym_eigh).
+void jacobi_eigh(cudaStream_t s, int k, double* S, double* Y, double* w, double* scratch, int* status,
+                 const int* skip = nullptr);
+// ---- trideig.cu : the Rayleigh-Ritz eigensolver.  Same contract as jacobi_eigh (S: upper triangle read, NOT
+// modified).  k >= 48: Householder tridiagonalisation + one warp per eigenpair (multisection, twisted
+// factorisation, back-transformation) + a-posteriori guard; Jacobi when the guard rejects or k is small.
+// scratch: >= sym_eigh_scratch_doubles(k).
+size_t sym_eigh_scratch_doubles(int k);
+void sym_eigh(cudaStream_t s, int k, double* S, double* Y, double* w, double* scratch, int* status);
+bool sym_eigh_uses_tridiag(int k);
+// guard outputs of the last sym_eigh call on this scratch: double[8] {max|S|, max|G-I|, max residual} + int accept
+double* sym_eigh_flags(double* scratch, int k);
 // T(:,j) = U(:,j) / sqrt(sv[j]); status |= 2 if some sv[j] <= 0 (not positive definite)
 void scale_cols_rsqrt_checked(cudaStream_t s, int k, const double* U, const double* sv, double* T, int* status);
 // D = diag(G)^-1/2 (0 where diag <= 0); G <- D G D

@@ -299,7 +299,7 @@ void dav_solver::alloc_work(int lowest, int kcap_) {
   Ap.alloc(kk); Bp.alloc(kk); Y.alloc(kk); G.alloc(kk); U.alloc(kk); Tm.alloc(kk); S1.alloc(kk); S2.alloc(kk);
   Z.alloc(kk);
   theta.alloc(kcap); sv.alloc(kcap); D.alloc(kcap); norms2.alloc(kcap);
-  jscratch.alloc(jacobi_scratch_doubles(kcap));
+  jscratch.alloc(sym_eigh_scratch_doubles(kcap));
   partial.alloc((size_t)kcap * 64);
   gemm_ws.alloc(std::max<size_t>(kk * 64, (size_t)1 << 22));
   small.alloc(16);
@@ -340,15 +340,15 @@ void dav_solver::rayleigh_ritz(int k, bool gev) {
   const int sp = begin_span(SPAN_RR);
   copy_matrix(stream, k, k, Ap.p, kcap, S1.p, k);
   if (!gev) {
-    jacobi_eigh(stream, k, S1.p, Y.p, theta.p, jscratch.p, status.p);
+    sym_eigh(stream, k, S1.p, Y.p, theta.p, jscratch.p, status.p);
   } else {
     copy_matrix(stream, k, k, Bp.p, kcap, S2.p, k);
-    jacobi_eigh(stream, k, S2.p, U.p, sv.p, jscratch.p, status.p);
+    sym_eigh(stream, k, S2.p, U.p, sv.p, jscratch.p, status.p);
     scale_cols_rsqrt_checked(stream, k, U.p, sv.p, Tm.p, status.p);
     symmetrize_from_upper(stream, k, S1.p, k);
     gemm(stream, false, k, k, k, 1.0, S1.p, k, Tm.p, k, 0.0, Z.p, k, nullptr, 0);
     gemm(stream, true, k, k, k, 1.0, Tm.p, k, Z.p, k, 0.0, S1.p, k, nullptr, 0);
-    jacobi_eigh(stream, k, S1.p, Z.p, theta.p, jscratch.p, status.p);
+    sym_eigh(stream, k, S1.p, Z.p, theta.p, jscratch.p, status.p);
     gemm(stream, false, k, k, k, 1.0, Tm.p, k, Z.p, k, 0.0, Y.p, k, nullptr, 0);
   }
   end_span(sp);
@@ -409,7 +409,7 @@ void dav_solver::orthonormalize_block(double* Cblk, int b, int kold, double* des
     const bool use_svqb = !tried_chol || h[2] != 0.0;
     if (use_svqb) {
       gram_prescale(stream, b, S1.p, D.p);
-      jacobi_eigh(stream, b, S1.p, U.p, sv.p, jscratch.p, status.p);
+      sym_eigh(stream, b, S1.p, U.p, sv.p, jscratch.p, status.p);
       svqb_make_T(stream, b, U.p, sv.p, D.p, Tm.p, flags.p);
       done = false;  // a rank-deficient / ill-conditioned pass is never the last one
     }
@@ -559,7 +559,7 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
         // the collapsed basis is B-orthonormal, not 2-orthonormal: restore V^T V = I (same span)
         gemm(stream, true, k0, k0, nl, 1.0, V.p, ldv, V.p, ldv, 0.0, S1.p, k0, gemm_ws.p, gemm_ws.n);
         allreduce(S1.p, (size_t)k0 * k0);
-        jacobi_eigh(stream, k0, S1.p, U.p, sv.p, jscratch.p, status.p);
+        sym_eigh(stream, k0, S1.p, U.p, sv.p, jscratch.p, status.p);
         scale_cols_rsqrt_checked(stream, k0, U.p, sv.p, Tm.p, status.p);
         for (double* Bf : bufs) {
           gemm(stream, false, nl, k0, k0, 1.0, Bf, ldv, Tm.p, k0, 0.0, T.p, ldv, nullptr, 0);

@@ -22,6 +22,19 @@ def lapack_generalized_eigensolver(mtx, stx=None):
     return w, v
 
 
+def sym_eigh_info(mtx, reps=0):
+    """Diagnostic of the Rayleigh-Ritz eigensolver (csrc/trideig.cu): returns (w, v, info, ms) with
+    info = {accepted, smax, orth_defect, residual}; accepted = -1 when the size goes to Jacobi directly."""
+    mtx = _f(mtx)
+    n = mtx.shape[0]
+    w = np.zeros(n)
+    v = np.zeros((n, n), order="F")
+    info = np.zeros(8)
+    ms = (C.c_float * max(reps, 1))()
+    check(lib().dav_sym_eigh_info(C.c_int(n), dp(mtx), dp(w), dp(v), dp(info), C.c_int(reps), ms))
+    return w, v, {"accepted": int(info[0]), "smax": info[1], "orth_defect": info[2], "residual": info[3], "prof": list(info[4:8])}, list(ms)[:reps]
+
+
 def lapack_generalized_eigensolver_lowest(mtx, stx, lowest):
     """lapack_generalized_eigensolver_lowest (lapack_wrapper.f90:93-174)."""
     mtx, stx = _f(mtx), _f(stx)

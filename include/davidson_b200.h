@@ -184,6 +184,12 @@ int dav_norm(int64_t n, const double* vector, double* result);
  * triangle read; stx may be NULL.  Device Jacobi. */
 int dav_lapack_generalized_eigensolver(int dim, const double* mtx, const double* stx, double* eigenvalues,
                                        double* eigenvectors);
+/* diagnostic / micro-benchmark of the Rayleigh-Ritz eigensolver on one dim x dim symmetric matrix (upper triangle
+ * read): runs it 1 + reps times, ms_out[reps] = CUDA-event time of each timed run (may be NULL with reps = 0),
+ * info[8] = {tridiagonal fast path accepted by the guard (1/0; -1 when dim uses Jacobi directly), max|S|,
+ * max|Y^T Y - I| before the Newton-Schulz step, max|S y - theta y|, 4 reserved (profiling builds)}. */
+int dav_sym_eigh_info(int dim, const double* mtx, double* eigenvalues, double* eigenvectors, double* info, int reps,
+                      float* ms_out);
 /* lapack_generalized_eigensolver_lowest (lapack_wrapper.f90:93-174) */
 int dav_lapack_generalized_eigensolver_lowest(int dim, const double* mtx, const double* stx, int lowest,
                                               double* eigenvalues, double* eigenvectors);

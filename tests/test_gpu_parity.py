@@ -8,6 +8,7 @@ import scipy.linalg as sl
 import fortran_davidson_b200 as fd
 from conftest import case_inputs
 from fortran_davidson_b200 import davidson as dv
+from fortran_davidson_b200 import lapack_wrapper as lw
 from fortran_davidson_b200._lib import DavidsonError
 from oracle import oracle as orc
 
@@ -242,6 +243,45 @@ def test_dense_device_generated_matches_uploaded():
     assert abs(iters - r.iters) <= 1
     _check_pairs(A, B, ev, vec, r.eigenvalues, r.eigenvectors, 1e-9)
     s.close()
+
+
+def _sym_cases():
+    rng = np.random.default_rng(11)
+    out = []
+    for k in (48, 64, 97, 128, 160, 200, 256, 320):
+        a = rng.standard_normal((k, k))
+        out.append(("random%d" % k, (a + a.T) / 2, True))
+    k = 128
+    out.append(("diagdom", np.diag(np.arange(1.0, k + 1)) + 1e-4 * (lambda r: (r + r.T) / 2)(rng.random((k, k))), True))
+    g = np.diag(np.concatenate([np.arange(1.0, 65), np.linspace(50, 1e5, 64)])) + 1e-2 * rng.standard_normal((k, k))
+    out.append(("graded", (g + g.T) / 2, True))
+    out.append(("near_identity", np.eye(k) + 1e-4 * (lambda r: (r + r.T) / 2)(rng.random((k, k))), True))
+    out.append(("identity", np.eye(k), False))                         # exactly degenerate -> Jacobi fallback
+    q, _ = np.linalg.qr(rng.standard_normal((k, k)))
+    out.append(("degenerate_pairs", (q * np.repeat(np.arange(1.0, 65), 2)) @ q.T, None))  # either path, must be right
+    out.append(("zero", np.zeros((64, 64)), None))
+    blk = np.zeros((96, 96)); blk[:48, :48] = out[0][1]; blk[48:, 48:] = out[0][1] + 3.0 * np.eye(48)
+    out.append(("block_diagonal", blk, None))
+    return out
+
+
+@pytest.mark.parametrize("case", _sym_cases(), ids=lambda c: c[0])
+def test_sym_eigh_tridiagonal_path(case):
+    """The Rayleigh-Ritz eigensolver (tridiagonalisation + multisection + twisted factorisation, guarded, Jacobi
+    fallback) against numpy's LAPACK: eigenvalues, orthonormality and residual at round-off level whichever
+    path produced them (lapack_wrapper.f90:14-91 contract: ascending eigenvalues, orthonormal vectors)."""
+    name, S, expect_fast = case
+    k = S.shape[0]
+    w, v, info, _ = lw.sym_eigh_info(np.triu(S))  # only the upper triangle may be read
+    ref = np.linalg.eigvalsh(S)
+    scale = max(np.abs(S).max(), 1e-300)
+    assert np.abs(w - ref).max() <= 1e-12 * k * scale, (name, info)
+    assert np.abs(v.T @ v - np.eye(k)).max() < 1e-12, (name, info)
+    assert np.abs(S @ v - v * w).max() <= 1e-12 * k * scale, (name, info)
+    if expect_fast is True:
+        assert info["accepted"] == 1, (name, info)
+    if expect_fast is False:
+        assert info["accepted"] == 0, (name, info)
 
 
 def test_upload_rows_matches_upload():
