@@ -89,7 +89,25 @@ __global__ void free_column_kernel(int op, int64_t n, int64_t col, const double*
     out[i] = (op == DAV_OP_IDENTITY) ? (i == col ? 1.0 : 0.0) : op_entry(op, i, col, etab);
 }
 
+__global__ void free_gather_columns_kernel(int op, int64_t n, int64_t row0, int64_t nl,
+                                           const double* __restrict__ etab, const int64_t* __restrict__ idx,
+                                           double* __restrict__ out, int64_t ldo) {
+  const int64_t col = idx[blockIdx.y];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nl; i += (int64_t)gridDim.x * blockDim.x)
+    out[i + (int64_t)blockIdx.y * ldo] =
+        (op == DAV_OP_IDENTITY) ? (row0 + i == col ? 1.0 : 0.0) : op_entry(op, row0 + i, col, etab);
+}
+
 }  // namespace
+
+void free_gather_columns_builtin(cudaStream_t s, int op, int64_t n, int64_t row0, int64_t nl, const double* etab,
+                                 const int64_t* idx, int k, double* out, int64_t ldo) {
+  if (nl <= 0 || k <= 0) return;
+  dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(nl, 256), 592)), (unsigned)k);
+  free_gather_columns_kernel<<<grid, 256, 0, s>>>(op, n, row0, nl, etab, idx, out, ldo);
+  CK_LAUNCH();
+  ++g_kernel_launches;
+}
 
 void free_matmul_builtin(cudaStream_t s, int op, int64_t n, int64_t row0, int64_t nl, int b, const double* etab,
                          const double* X, int64_t ldx, double* W, int64_t ldw) {

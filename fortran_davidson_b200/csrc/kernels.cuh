@@ -34,6 +34,18 @@ void free_diag_builtin(cudaStream_t s, int op, int64_t n, int64_t row0, int64_t 
 void free_column_builtin(cudaStream_t s, int op, int64_t n, int64_t col /*0-based*/, const double* etab,
                          double* out);
 
+// out(:, j) = Op(rows row0..row0+nl, idx[j]) : A*V for a one-hot V without generating the whole operator
+void free_gather_columns_builtin(cudaStream_t s, int op, int64_t n, int64_t row0, int64_t nl, const double* etab,
+                                 const int64_t* idx, int k, double* out, int64_t ldo);
+// ---- freeops_dmma.cu : the same operators on the FP64 tensor pipe (entries from a piecewise polynomial) ----------
+struct FreeTables;  // (e_t, 1/e_t) table + polynomial coefficients + packed-X scratch of one operator
+FreeTables* free_tables_create(int op, int64_t n, const double* etab_host);
+void free_tables_destroy(FreeTables* t);
+bool free_tables_usable(const FreeTables* t);   // false: the fitted table failed its accuracy check
+double free_tables_max_err(const FreeTables* t);
+void free_matmul_dmma(cudaStream_t s, FreeTables* t, int64_t row0, int64_t nl, int b, const double* X, int64_t ldx,
+                      double* W, int64_t ldw);
+
 // ---- smalldense.cu : k x k problems on one CTA ----------------------------------------------------
 // Two-sided Jacobi, round-robin parallel ordering.  S: k x k (ld k), upper triangle read, destroyed.
 // Y: k x k eigenvectors sorted by ascending eigenvalue w.  status: device int, set nonzero on failure

@@ -23,6 +23,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <thread>
+#include <vector>
 
 using namespace dav;
 
@@ -53,11 +55,41 @@ dav_solver::dav_solver(int device_, int rank, int world, const void* id128) : de
 
 dav_solver::~dav_solver() {
   cudaSetDevice(device);
-  for (int w = 0; w < 2; ++w)
+  for (int w = 0; w < 2; ++w) {
     if (mat[w].plan) matvec_plan_destroy(mat[w].plan);
+    if (mat[w].ftab) free_tables_destroy(mat[w].ftab);
+  }
   for (cudaEvent_t ev : ev_pool) cudaEventDestroy(ev);
+  if (pinned_out) cudaFreeHost(pinned_out);
   if (stream) cudaStreamDestroy(stream);
 }
+
+double* dav_solver::pinned(size_t count) {
+  if (count <= pinned_out_n && pinned_out) return pinned_out;
+  if (pinned_out) cudaFreeHost(pinned_out);
+  pinned_out = nullptr;
+  pinned_out_n = 0;
+  CK(cudaMallocHost((void**)&pinned_out, count * sizeof(double)));
+  pinned_out_n = count;
+  return pinned_out;
+}
+
+namespace {
+// pinned staging -> caller's array, column by column, split over a few host threads for large blocks
+void copy_out(const double* src, int64_t rows, int cols, double* dst, int64_t ldd) {
+  const size_t bytes = (size_t)rows * cols * 8;
+  const int nthreads = bytes > ((size_t)4 << 20) ? std::min(4, cols) : 1;
+  auto work = [&](int t) {
+    for (int j = t; j < cols; j += nthreads)
+      std::memcpy(dst + (size_t)j * ldd, src + (size_t)j * rows, (size_t)rows * 8);
+  };
+  if (nthreads == 1) { work(0); return; }
+  std::vector<std::thread> th;
+  for (int t = 1; t < nthreads; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto& x : th) x.join();
+}
+}  // namespace
 
 void dav_solver::set_dims(int64_t n_) {
   if (n_ <= 0) DAV_THROW(DAV_ERR_INVALID, "matrix dimension must be positive");
@@ -77,6 +109,8 @@ void dav_solver::clear_matrix(int which) {
   Matrix& m = mat[which];
   if (m.plan) matvec_plan_destroy(m.plan);
   m.plan = nullptr;
+  if (m.ftab) free_tables_destroy(m.ftab);
+  m.ftab = nullptr;
   m.A.release();
   m.diag.release();
   m.diag_valid = false;
@@ -171,7 +205,8 @@ void dav_solver::ensure_etab() {
   if (etab.n == (size_t)n && etab.p) return;
   // e_t = dble(exp(real(t)/real(dim))) in SINGLE precision (benchmark_free.f90:50,53) -- built with the
   // host's expf so the table carries exactly the bits the oracle (and gfortran) see.
-  std::vector<double> h((size_t)n);
+  std::vector<double>& h = etab_host;
+  h.resize((size_t)n);
   const float fn = (float)n;
   for (int64_t t = 0; t < n; ++t) h[(size_t)t] = (double)expf((float)(t + 1) / fn);
   etab.release();
@@ -268,7 +303,20 @@ void dav_solver::apply_full(int which, const double* Xf, int64_t ldx, int b, dou
       gemm(stream, false, nl, b, n, 1.0, m.A.p, m.lda, Xf, ldx, 0.0, W, ldw, nullptr, 0);
   } else if (m.kind == BUILTIN) {
     ensure_etab();
-    free_matmul_builtin(stream, m.op, n, row0, nl, b, etab.p, Xf, ldx, W, ldw);
+    // tensor-pipe generator unless the SIMT reference kernel is forced (or the fitted table failed its check)
+    if (m.op != DAV_OP_IDENTITY && matvec_impl != DAV_MATVEC_SIMT) {
+      if (!m.ftab || (int64_t)etab_host.size() != n) {
+        if (m.ftab) free_tables_destroy(m.ftab);
+        m.ftab = free_tables_create(m.op, n, etab_host.data());
+      }
+      if (matvec_impl == DAV_MATVEC_TMA_DMMA && !free_tables_usable(m.ftab))
+        DAV_THROW(DAV_ERR_CUDA, "free operator: polynomial table failed its accuracy check (max error %.3e)",
+                  free_tables_max_err(m.ftab));
+    }
+    if (m.ftab && free_tables_usable(m.ftab) && m.op != DAV_OP_IDENTITY && matvec_impl != DAV_MATVEC_SIMT)
+      free_matmul_dmma(stream, m.ftab, row0, nl, b, Xf, ldx, W, ldw);
+    else
+      free_matmul_builtin(stream, m.op, n, row0, nl, b, etab.p, Xf, ldx, W, ldw);
   } else if (m.kind == CALLBACK) {
     host_x.resize((size_t)n * b);
     host_y.resize((size_t)n * b);
@@ -441,6 +489,7 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
   int kc = std::max(k0, 2 * max_dim);
   if ((int64_t)kc > n) kc = (int)std::max<int64_t>(k0, n);
   alloc_work(L, kc);
+  if (eigenvectors) pinned((size_t)(comm.active() ? n : std::max<int64_t>(nl, 1)) * L);  // outside the timed span
 
   std::memset(&stats, 0, sizeof(stats));
   spans.clear();
@@ -475,6 +524,11 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
       sp = begin_span(SPAN_INIT);
       gather_columns(stream, mat[w].A.p, mat[w].lda, nl, idx.p, k, W, ldv);  // A*V for one-hot V
       end_span(sp);
+    } else if (mat[w].kind == BUILTIN) {
+      sp = begin_span(SPAN_INIT);
+      ensure_etab();
+      free_gather_columns_builtin(stream, mat[w].op, n, row0, nl, etab.p, idx.p, k, W, ldv);  // Op*V, one-hot V
+      end_span(sp);
     } else {
       Xfull.alloc((size_t)n * k);
       fill_zero(stream, Xfull.p, (size_t)n * k);
@@ -492,12 +546,18 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
   for (it = 1; it <= max_iterations; ++it) {
     rayleigh_ritz(k, gev);                                            // step 3
     sp = begin_span(SPAN_RESID);
-    // step 4.1 from the stored products: R = AV*Y - (BV|V)*Y*diag(theta), all k columns
-    gemm(stream, false, nl, k, k, 1.0, AV.p, ldv, Y.p, k, 0.0, R.p, ldv, nullptr, 0);
-    gemm(stream, false, nl, k, k, 1.0, gev ? BV.p : V.p, ldv, Y.p, k, 0.0, C.p, ldv, nullptr, 0);
-    residual_dpr(stream, nl, k, R.p, ldv, C.p, ldv, theta.p, mat[0].diag.p, gev ? mat[1].diag.p : nullptr,
-                 method == DAV_METHOD_DPR, partial.p, norms2.p);
-    allreduce(norms2.p, k);
+    // step 4.1 from the stored products: R = AV*Y - (BV|V)*Y*diag(theta).  The reference forms all k residuals and
+    // then tests the first L (davidson.f90:163-178); here the first L columns come first and the other k-L (needed
+    // only for the corrections of a NEXT iteration) are skipped when the test passes or the iteration budget ends.
+    auto residual_cols = [&](int c0, int nc) {
+      gemm(stream, false, nl, nc, k, 1.0, AV.p, ldv, Y.p + (size_t)c0 * k, k, 0.0, R.p + (size_t)c0 * ldv, ldv, nullptr, 0);
+      gemm(stream, false, nl, nc, k, 1.0, gev ? BV.p : V.p, ldv, Y.p + (size_t)c0 * k, k, 0.0, C.p + (size_t)c0 * ldv,
+           ldv, nullptr, 0);
+      residual_dpr(stream, nl, nc, R.p + (size_t)c0 * ldv, ldv, C.p + (size_t)c0 * ldv, ldv, theta.p + c0,
+                   mat[0].diag.p, gev ? mat[1].diag.p : nullptr, method == DAV_METHOD_DPR, partial.p, norms2.p + c0);
+      allreduce(norms2.p + c0, nc);
+    };
+    residual_cols(0, L);
     end_span(sp);
     CK(cudaMemcpyAsync(hn2.data(), norms2.p, (size_t)L * 8, cudaMemcpyDeviceToHost, stream));
     check_status("Rayleigh-Ritz");  // synchronises the stream
@@ -522,17 +582,27 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
       // eigenvalues = theta(1:L), eigenvectors = V*Y(:, 1:L) of this Rayleigh-Ritz step (:186-187)
       gemm(stream, false, nl, L, k, 1.0, V.p, ldv, Y.p, k, 0.0, T.p, ldv, nullptr, 0);
       CK(cudaMemcpyAsync(eigenvalues, theta.p, (size_t)L * 8, cudaMemcpyDeviceToHost, stream));
+      int64_t out_rows = 0;
+      double* stage = nullptr;
       if (eigenvectors) {
         int64_t ldf = 0;
         const double* Xf = gather_rows(T.p, ldv, L, &ldf);
-        const int64_t rows = comm.active() ? n : nl;
-        CK(cudaMemcpy2DAsync(eigenvectors, (size_t)ldvec * 8, Xf, (size_t)ldf * 8, (size_t)rows * 8, (size_t)L,
+        out_rows = comm.active() ? n : nl;
+        stage = pinned((size_t)out_rows * L);
+        CK(cudaMemcpy2DAsync(stage, (size_t)out_rows * 8, Xf, (size_t)ldf * 8, (size_t)out_rows * 8, (size_t)L,
                              cudaMemcpyDeviceToHost, stream));
       }
       CK(cudaStreamSynchronize(stream));
+      if (eigenvectors) copy_out(stage, out_rows, L, eigenvectors, ldvec);
       if (converged) break;
     }
     if (it == max_iterations) { it = max_iterations + 1; break; }
+    if (k > L && k <= max_dim) {  // residuals + corrections of the remaining Ritz pairs: every Ritz pair is
+                                  // expanded (davidson.f90:196-206); a collapse step uses none of them
+      sp = begin_span(SPAN_RESID);
+      residual_cols(L, k - L);
+      end_span(sp);
+    }
 
     if (k <= max_dim) {                                               // step 5 (:195)
       if ((int64_t)2 * k > n || 2 * k > kcap)

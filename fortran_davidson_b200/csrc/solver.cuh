@@ -15,6 +15,7 @@ struct dav_solver {
     int64_t lda = 0;
     dav::MatvecPlan* plan = nullptr;
     int op = 0;                      // BUILTIN
+    dav::FreeTables* ftab = nullptr; // BUILTIN: tables of the tensor-pipe generator (freeops_dmma.cu)
     dav_gemv_fn fn = nullptr;        // CALLBACK
     void* ctx = nullptr;
     dav::DevBuf<double> diag;        // local diagonal entries
@@ -27,6 +28,7 @@ struct dav_solver {
   int64_t n = 0, nl = 0, row0 = 0, chunk = 0;  // global size, local rows, first local row, rows per rank
   Matrix mat[2];
   dav::DevBuf<double> etab;  // e_t table of the built-in operators
+  std::vector<double> etab_host;
   int matvec_impl = DAV_MATVEC_AUTO;
   dav_stats_t stats;
 
@@ -40,6 +42,11 @@ struct dav_solver {
   dav::DevBuf<int64_t> idx, cand_idx, topk_idx;
   dav::DevBuf<double> cand_val, topk_val;
   std::vector<double> host_x, host_y;  // callback staging
+  // page-locked staging of the eigenvectors on their way to the caller's (pageable) array: a direct device ->
+  // pageable copy runs at ~6 GB/s (2 ms for the 12.8 MB of n = 100,000 x 16), through here at PCIe speed
+  double* pinned_out = nullptr;
+  size_t pinned_out_n = 0;
+  double* pinned(size_t count);
   std::vector<cudaEvent_t> ev_pool;
   struct Span { int a, b, kind; };
   std::vector<Span> spans;

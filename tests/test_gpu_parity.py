@@ -54,6 +54,24 @@ def test_free_matmul_matches_oracle(op, n, b):
     assert np.abs(w - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("op", [dv.OP_BENCHMARK_MTX, dv.OP_TEST_MTX, dv.OP_TEST_STX])
+@pytest.mark.parametrize("n,b", [(257, 8), (3000, 16), (5000, 40), (4097, 64), (3001, 100), (2500, 128), (2000, 200)])
+def test_free_matmul_tensor_pipe_matches_libm_kernel(op, n, b):
+    """The tensor-pipe generator (piecewise polynomial entries + DMMA, csrc/freeops_dmma.cu) against the SIMT
+    kernel that evaluates atan2/log/sqrt/cos with libm, on the same operator (benchmark_free.f90:38-76)."""
+    x = np.random.default_rng(n * 7 + b).standard_normal((n, b))
+    s = fd.DavidsonSolver()
+    s.set_operator(0, n, op)
+    s.set_matvec_impl(dv.MATVEC_SIMT)
+    ref = s.block_matvec(0, x)
+    s.set_matvec_impl(dv.MATVEC_TMA_DMMA)
+    w = s.block_matvec(0, x)
+    s.close()
+    assert np.abs(w - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
+    if n <= 3000:
+        assert np.abs(w - orc.free_matmul(op, x)).max() <= 1e-13 * max(1.0, np.abs(ref).max())
+
+
 # ---------------------------------------------------------------- block matvec
 @pytest.mark.parametrize("impl", [dv.MATVEC_SIMT, dv.MATVEC_TMA_DMMA])
 @pytest.mark.parametrize("n,b", [(50, 6), (300, 1), (1000, 5), (1024, 8), (2000, 20), (4097, 33), (3000, 64),
