@@ -43,6 +43,10 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--matvec-impl", type=int, default=0)
+    # the other BASELINE.json configs (profiles only; the driver runs the default = configs[2])
+    ap.add_argument("--method", default="DPR", choices=["DPR", "GJD"])
+    ap.add_argument("--gev", action="store_true", help="second_matrix = generate_diagonal_dominant(n, sparsity, 1.0), seed 1")
+    ap.add_argument("--free", action="store_true", help="matrix-free benchmark_free operator, stx = identity")
     return ap.parse_args()
 
 
@@ -103,6 +107,20 @@ def measured_peaks():
     return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md), MEASURED_PEAKS.json absent"
 
 
+def measured_traffic(args, b):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the matvec kernel per launch from the committed ncu capture
+    (profiles/r01_matvec_traffic.json); only for the exact shape that was captured (n, 1 GPU, dense)."""
+    if args.free or args.gpus != 1:
+        return None
+    p = os.path.join(ROOT, "profiles", "r01_matvec_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    if int(d.get("n", -1)) != args.n or str(b) not in d.get("bytes_per_launch", {}):
+        return None
+    return {"bytes": float(d["bytes_per_launch"][str(b)]), "source": d.get("source", "profiles/")}
+
+
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_run(args, steps, warmup, budget_s):
     """Times the oracle (CPU restatement of the reference + real LAPACK) on the host cores on a bounded
@@ -149,12 +167,32 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def metric_name(args):
+    if args.free:
+        return "time_to_converge_matrix_free_n%d_lowest%d_%s" % (args.n, args.lowest, args.method)
+    if args.gev or args.method != "DPR" or args.n != 100000 or args.lowest != 16:
+        return "time_to_converge_dense_fp64_n%d_lowest%d_%s%s" % (args.n, args.lowest, args.method,
+                                                                 "_second_matrix" if args.gev else "")
+    return METRIC
+
+
 def workload_config(args, n_gpus):
     md = args.max_dim or 10 * args.lowest
-    return {"workload": "BASELINE.json configs[2]: dense fp64 generate_diagonal_dominant(n=%d, sparsity=%g, seed 0), "
-                        "lowest=%d, DPR, max_dim_sub=%d, tol=%g, row-block sharded over %d GPU(s)"
-                        % (args.n, args.sparsity, args.lowest, md, args.tol, n_gpus),
-            "n": args.n, "lowest": args.lowest, "method": "DPR", "max_dim_sub": md, "tolerance": args.tol,
+    if args.free:
+        return {"workload": "BASELINE.json configs[4]-shape: matrix-free benchmark_free operator (benchmark_free.f90:38-76) "
+                            "n=%d, stx = identity, lowest=%d, DPR, max_dim_sub=%d, tol=%g, rows sharded over %d GPU(s)"
+                            % (args.n, args.lowest, md, args.tol, n_gpus),
+                "n": args.n, "lowest": args.lowest, "method": "DPR", "max_dim_sub": md, "tolerance": args.tol,
+                "l2_policy": "operator entries are generated in shared memory; X block re-read from L2",
+                "parallelism": "row-block x%d" % n_gpus}
+    which = "configs[2]" if (args.n == 100000 and not args.gev) else ("configs[3]" if args.gev else "configs[1]-shape")
+    return {"workload": "BASELINE.json %s: dense fp64 generate_diagonal_dominant(n=%d, sparsity=%g, seed 0)%s, "
+                        "lowest=%d, %s, max_dim_sub=%d, tol=%g, row-block sharded over %d GPU(s)"
+                        % (which, args.n, args.sparsity,
+                           " + second_matrix generate_diagonal_dominant(n, sparsity, 1.0, seed 1)" if args.gev else "",
+                           args.lowest, args.method, md, args.tol, n_gpus),
+            "n": args.n, "lowest": args.lowest, "method": args.method, "max_dim_sub": md, "tolerance": args.tol,
+            "second_matrix": bool(args.gev),
             "l2_policy": "matrix (%.1f GB) is far larger than L2 (126 MB): no flush needed" % (8e-9 * args.n * args.n),
             "parallelism": "row-block x%d" % n_gpus}
 
@@ -203,13 +241,19 @@ def main():
     n, L = args.n, args.lowest
     md = args.max_dim or None
     t0 = time.perf_counter()
-    solver.generate_diagonal_dominant(0, n, args.sparsity, None, 0)
+    if args.free:
+        solver.set_operator(0, n, fd.OP_BENCHMARK_MTX)
+        solver.set_operator(1, n, fd.OP_IDENTITY)
+    else:
+        solver.generate_diagonal_dominant(0, n, args.sparsity, None, 0)
+        if args.gev:
+            solver.generate_diagonal_dominant(1, n, args.sparsity, 1.0, 1)
     barrier()
     gen_s = time.perf_counter() - t0
 
     # ---- warm-up
     for _ in range(args.warmup):
-        ev, _vec, iters = solver.solve(L, "DPR", 1000, args.tol, md, want_vectors=True)
+        ev, _vec, iters = solver.solve(L, args.method, 1000, args.tol, md, want_vectors=True, pinned=True)
 
     # ---- timed region: exactly K solves, barrier + synchronize on both sides, device time = CUDA events on the
     # solver's own stream (dav_stats_t.solve_ms), max over ranks
@@ -219,7 +263,7 @@ def main():
     with ClockSampler(local_rank) as clocks:
         w0 = time.perf_counter()
         for _ in range(args.steps):
-            ev, vec, iters = solver.solve(L, "DPR", 1000, args.tol, md, want_vectors=True)
+            ev, vec, iters = solver.solve(L, args.method, 1000, args.tol, md, want_vectors=True, pinned=True)
             st = solver.stats()
             dev_ms.append(st.solve_ms)
             mv_ms.append(st.matvec_ms)
@@ -235,7 +279,8 @@ def main():
     # ---- residual check of the result (property at full size): ||A v - lambda v|| <= tol
     av = solver.block_matvec(0, vec)
     r0, r1 = solver.rows()
-    res2 = ((av - vec[r0:r1] * ev) ** 2).sum(axis=0)
+    bv = solver.block_matvec(1, vec) if (args.gev and not args.free) else vec[r0:r1]
+    res2 = ((av - bv * ev) ** 2).sum(axis=0)
     if distributed:
         t = torch.tensor(res2, dtype=torch.float64, device="cuda")
         dist.all_reduce(t)
@@ -248,7 +293,7 @@ def main():
     widths = sorted(set([16] + [int(k) for k in st.trace_k[:max(st.trace_len - 1, 1)]]))
     per_width = {}
     for b in widths:
-        ms = solver.bench_block_matvec(0, b, 5)
+        ms = solver.bench_block_matvec(0, b, 2 if args.free else 5)
         ms_b = max_over_ranks(float(np.median(ms)))
         byts = 8.0 * nl * n + 8.0 * n * b + 8.0 * nl * b
         per_width[str(b)] = {"ms": ms_b, "GBps": byts / ms_b * 1e-6, "TFLOPs": 2.0 * nl * n * b / ms_b * 1e-9,
@@ -280,7 +325,20 @@ def main():
                 "per_width": per_width, "matvec_ms_in_solve": in_solve_ms,
                 "matvec_share_of_step": in_solve_ms / ms_per_step}
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    if args.free:
+        for v in per_width.values():
+            v["Gentries_per_s"] = 1e-6 * nl * n / v["ms"]
+            v.pop("GBps", None); v.pop("hbm_frac", None)
+        roofline["hbm_view"] = None
+        roofline["kernel"] = ("free_dmma_kernel (operator entries generated into swizzled shared memory by a piecewise "
+                              "polynomial, FP64 DMMA against the packed X tile), widest block b=%d: 2*nl*n*b flops / launch; "
+                              "bound = FP64 pipe shared by DMMA and the generator" % dom_b)
+    traffic = measured_traffic(args, dom_b)
+    if traffic is not None:
+        roofline["traffic"] = traffic["bytes"]
+        roofline["traffic_source"] = traffic["source"]
+        roofline["algorithmic_bytes"] = 8.0 * nl * n + 8.0 * n * dom_b + 8.0 * nl * dom_b
+    line = {"metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, args.gpus),
             "iterations": int(iters) if iters is not None else None,
@@ -288,13 +346,16 @@ def main():
             "eigenvalues_head": [float(x) for x in ev[:4]], "max_residual": max_res,
             "wall_ms_per_step": wall_ms, "generate_s": gen_s,
             "phase_ms": {"matvec": st.matvec_ms, "rayleigh_ritz": st.rr_ms, "orthonormalise": st.orth_ms,
-                         "residual_dpr": st.resid_ms, "projection": st.proj_ms, "init": st.init_ms},
+                         "residual_dpr": st.resid_ms, "projection": st.proj_ms, "init": st.init_ms,
+                         "gather_new_block": st.gather_ms, "output_vectors": st.output_ms},
             "gpu_launches": int(sum(launches) / len(launches)), "matvec_launches": int(mv_launch[-1]),
             "clocks": clocks.summary(), "roofline": roofline}
 
     # ---- end to end through the drop-in C ABI with HOST buffers (upload inside the timed region)
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and (args.free or args.gev):
+        e2e = {"value": None, "unit": UNIT, "skipped": "e2e is measured on the default workload only"}
+    elif not args.no_e2e:
         try:
             e2e = run_e2e(args, solver, fd, torch, dist, distributed, rank, world, n, L, md, barrier, max_over_ranks)
         except Exception as ex:  # report, never fake
@@ -302,7 +363,7 @@ def main():
     line["e2e"] = e2e if e2e is not None else {"value": None, "unit": UNIT, "skipped": "--no-e2e"}
 
     # ---- CPU baseline on the box's host cores (rank 0, N=1 only)
-    if rank == 0 and args.gpus == 1 and not args.no_cpu:
+    if rank == 0 and args.gpus == 1 and not args.no_cpu and not (args.free or args.gev or args.method != "DPR"):
         try:
             line["cpu_baseline"] = cpu_reference_run(args, 1, 0, budget_s=25.0)
         except Exception as ex:
@@ -355,7 +416,7 @@ def run_e2e(args, solver, fd, torch, dist, distributed, rank, world, n, L, md, b
         else:
             # sharded: every rank uploads its own row block from its own page-locked host copy
             solver.upload_rows_ptr(0, n, ptr, nl)
-            ev, _v, _it = solver.solve(L, "DPR", 1000, args.tol, md, want_vectors=True)
+            ev, _v, _it = solver.solve(L, args.method, 1000, args.tol, md, want_vectors=True, pinned=True)
             solver.clear(0)
         barrier()
         if i > 0:

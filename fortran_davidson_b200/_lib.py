@@ -15,7 +15,7 @@ GEMV_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_in
 SYMBOLS = [
     "dav_last_error", "dav_version", "dav_device_count", "dav_generalized_eigensolver_dense",
     "dav_generalized_eigensolver_free", "dav_generalized_eigensolver_free_builtin", "dav_get_unique_id",
-    "dav_create", "dav_create_distributed", "dav_destroy", "dav_partition_rows",
+    "dav_create", "dav_create_distributed", "dav_destroy", "dav_alloc_pinned", "dav_free_pinned", "dav_partition_rows",
     "dav_matrix_generate_diagonal_dominant", "dav_matrix_upload", "dav_matrix_upload_rows",
     "dav_matrix_set_operator",
     "dav_matrix_set_callback", "dav_matrix_clear", "dav_matrix_download", "dav_solve", "dav_get_stats",
@@ -33,7 +33,7 @@ class Stats(C.Structure):
         ("iterations", C.c_int), ("trace_len", C.c_int), ("trace_k", C.c_int * 64), ("trace_err", C.c_double * 64),
         ("last_matvec_b", C.c_int), ("last_matvec_ms", C.c_double), ("rr_ms", C.c_double), ("orth_ms", C.c_double),
         ("resid_ms", C.c_double), ("proj_ms", C.c_double), ("init_ms", C.c_double),
-        ("gjd_inner_iterations", C.c_int),
+        ("gjd_inner_iterations", C.c_int), ("gather_ms", C.c_double), ("output_ms", C.c_double),
     ]
 
 

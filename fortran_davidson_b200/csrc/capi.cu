@@ -121,6 +121,19 @@ int dav_device_count(void) {
   return count;
 }
 
+int dav_alloc_pinned(size_t bytes, void** ptr) {
+  API_BEGIN
+  need(ptr != nullptr && bytes > 0, "bad arguments");
+  CK(cudaMallocHost(ptr, bytes));
+  API_END
+}
+
+int dav_free_pinned(void* ptr) {
+  API_BEGIN
+  if (ptr) CK(cudaFreeHost(ptr));
+  API_END
+}
+
 int dav_partition_rows(int64_t n, int world_size, int rank, int64_t* row_begin, int64_t* row_end) {
   if (n < 0 || world_size < 1 || rank < 0 || rank >= world_size || !row_begin || !row_end) {
     dav::set_last_error("dav_partition_rows: bad arguments");

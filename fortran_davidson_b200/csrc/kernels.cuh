@@ -81,6 +81,10 @@ void cholesky_upper(cudaStream_t s, int k, double* G, int64_t ld, int* status);
 // G (b x b, ld b, only read) = R^T R; T <- R^-1 (dense, upper).  flag[0] (device double) <- 1.0 if a pivot is not
 // safely positive, else 0.0.  Returns false (nothing launched) when b is too large for shared memory.
 bool chol_inv_upper(cudaStream_t s, int b, const double* G, double* T, double* flag);
+// fused block orthonormalisation helpers (see solver.cu::orthonormalize_block_pip)
+void pip_prepare(cudaStream_t s, int k, int b, const double* Gall, const double* P, double* Gs, double* D,
+                 double* metrics);
+void pip_finish(cudaStream_t s, int k, int b, const double* Tinv, const double* D, double* Tm, double* M);
 // Rinv = inverse of the upper triangular R (k x k)
 void invert_upper(cudaStream_t s, int k, const double* R, int64_t ld, double* Rinv);
 

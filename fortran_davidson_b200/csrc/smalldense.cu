@@ -573,7 +573,81 @@ __global__ void invert_upper_kernel(int k, const double* __restrict__ R, int64_t
   }
 }
 
+// ---- fused block orthonormalisation (BCGS with the Pythagorean inner product) ---------------------------------
+// Gall ((k+b) x b, ld k+b): rows 0..k = H = V^T C, rows k.. = C^T C.  P = H^T H.  Forms the Gram matrix of the
+// projected block G' = C^T C - H^T H, scales it to unit diagonal (Gs = D G' D, D = diag(G')^-1/2), and measures how
+// far the block was from being orthonormal to V and to itself:
+//   metrics[0] = max_kj |H_kj| / sqrt((C^T C)_jj)      metrics[1] = max_ij |Gs_ij - delta_ij|
+//   metrics[2] = 1.0 when a diagonal entry of G' is not safely positive (block numerically inside span(V))
+__global__ void __launch_bounds__(1024) pip_prepare_kernel(int k, int b, const double* __restrict__ Gall,
+                                                           const double* __restrict__ P, double* __restrict__ Gs,
+                                                           double* __restrict__ D, double* __restrict__ metrics) {
+  extern __shared__ __align__(16) double sm[];
+  double* dsc = sm;       // b: D
+  double* cn = sm + b;    // b: 1 / sqrt((C^T C)_jj)
+  __shared__ double red[32];
+  __shared__ int bad;
+  const int ld = k + b, tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) bad = 0;
+  __syncthreads();
+  for (int j = tid; j < b; j += nt) {
+    const double cc = Gall[(size_t)j * ld + k + j];
+    const double d = cc - P[(size_t)j * b + j];
+    // the projected column must keep a safe fraction of its norm, otherwise G' is round-off
+    if (!(cc > 0.0) || !(d > 1e-10 * cc)) { bad = 1; dsc[j] = 0.0; cn[j] = 0.0; }
+    else { dsc[j] = rsqrt(d); cn[j] = rsqrt(cc); }
+  }
+  __syncthreads();
+  double m1 = 0.0, m0 = 0.0;
+  for (int e = tid; e < b * b; e += nt) {
+    const int i = e % b, j = e / b;
+    const double g = (Gall[(size_t)j * ld + k + i] - P[e]) * dsc[i] * dsc[j];
+    Gs[e] = g;
+    const double dev = fabs(g - (i == j ? 1.0 : 0.0));
+    m1 = (dev == dev) ? fmax(m1, dev) : 1.0e300;
+  }
+  for (int e = tid; e < k * b; e += nt) {
+    const int i = e % k, j = e / k;
+    const double h = fabs(Gall[(size_t)j * ld + i]) * cn[j];
+    m0 = (h == h) ? fmax(m0, h) : 1.0e300;
+  }
+  for (int j = tid; j < b; j += nt) D[j] = dsc[j];
+  m0 = block_reduce_max(m0, red);
+  m1 = block_reduce_max(m1, red);
+  if (tid == 0) {
+    metrics[0] = m0;
+    metrics[1] = m1;
+    metrics[2] = bad ? 1.0 : 0.0;
+  }
+}
+
+// M ((k+b) x b, ld k+b): rows k.. <- Tm = diag(D) * Tinv (upper triangular); Tm also stored densely (b x b) for the
+// product H * Tm that fills rows 0..k.
+__global__ void pip_finish_kernel(int k, int b, const double* __restrict__ Tinv, const double* __restrict__ D,
+                                  double* __restrict__ Tm, double* __restrict__ M) {
+  const int ld = k + b;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < b * b; e += gridDim.x * blockDim.x) {
+    const int i = e % b, j = e / b;
+    const double t = Tinv[e] * D[i];
+    Tm[e] = t;
+    M[(size_t)j * ld + k + i] = t;
+  }
+}
+
 }  // namespace
+
+void pip_prepare(cudaStream_t s, int k, int b, const double* Gall, const double* P, double* Gs, double* D,
+                 double* metrics) {
+  pip_prepare_kernel<<<1, 1024, 2 * (size_t)b * sizeof(double), s>>>(k, b, Gall, P, Gs, D, metrics);
+  CK_LAUNCH();
+  ++g_kernel_launches;
+}
+
+void pip_finish(cudaStream_t s, int k, int b, const double* Tinv, const double* D, double* Tm, double* M) {
+  pip_finish_kernel<<<std::max(1, std::min(64, (b * b + 255) / 256)), 256, 0, s>>>(k, b, Tinv, D, Tm, M);
+  CK_LAUNCH();
+  ++g_kernel_launches;
+}
 
 void jacobi_eigh(cudaStream_t s, int k, double* S, double* Y, double* w, double* scratch, int* status,
                  const int* skip) {

@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -29,7 +30,8 @@
 using namespace dav;
 
 namespace {
-enum { SPAN_MATVEC = 0, SPAN_RR = 1, SPAN_ORTH = 2, SPAN_RESID = 3, SPAN_PROJ = 4, SPAN_INIT = 5, SPAN_TOTAL = 6 };
+enum { SPAN_MATVEC = 0, SPAN_RR = 1, SPAN_ORTH = 2, SPAN_RESID = 3, SPAN_PROJ = 4, SPAN_INIT = 5, SPAN_TOTAL = 6,
+       SPAN_GATHER = 7, SPAN_OUT = 8 };
 constexpr int EV_POOL = 1024;
 }  // namespace
 
@@ -252,6 +254,9 @@ void dav_solver::ensure_plan(int which, int max_b) {
 }
 
 int dav_solver::begin_span(int kind) {
+  // DAV_NO_SPANS=1: only the total is timed (the per-phase events cost two cudaEventRecord calls per span)
+  static const bool no_spans = [] { const char* e = std::getenv("DAV_NO_SPANS"); return e && std::atoi(e) != 0; }();
+  if (no_spans && kind != SPAN_TOTAL) return -1;
   if (ev_used + 2 > (int)ev_pool.size()) {
     if ((int)ev_pool.size() >= EV_POOL) return -1;
     for (int i = 0; i < 64; ++i) {
@@ -288,7 +293,9 @@ const double* dav_solver::gather_rows(const double* Xlocal, int64_t ldx, int b, 
 
 void dav_solver::apply(int which, const double* Xlocal, int64_t ldx, int b, double* W, int64_t ldw) {
   int64_t ldf = 0;
+  const int spg = begin_span(SPAN_GATHER);
   const double* Xf = gather_rows(Xlocal, ldx, b, &ldf);
+  end_span(spg);
   apply_full(which, Xf, ldf, b, W, ldw);
 }
 
@@ -470,6 +477,57 @@ void dav_solver::orthonormalize_block(double* Cblk, int b, int kold, double* des
   end_span(sp);
 }
 
+// Fast path of the block orthonormalisation: the new block sits in V(:, kold : kold+b), i.e. [V | C] is ONE
+// contiguous nl x (kold+b) array.  Two passes of block classical Gram-Schmidt with the Pythagorean inner product
+// (BCGS-PIP2): per pass ONE tall-skinny product [V C]^T C (projection coefficients H and Gram matrix together, one
+// all-reduce), the small factorisation G' = C^T C - H^T H = R^T R on one CTA, and ONE tall-skinny update
+// C <- [V C] [-H R^-1; R^-1].  No host round trip until the flags of both passes are read once, before the last
+// update; pass 2 starts from a block that is orthonormal to ~eps cond^2, so it ends orthonormal to O(eps) whenever
+// the measured defects of its input are below 1e-6.  Returns false (block untouched) when a pivot is unsafe or the
+// defects are too large: the caller then runs the SVQB loop of orthonormalize_block on the same block.
+bool dav_solver::orthonormalize_block_pip(int b, int kold) {
+  const int kb = kold + b;
+  if (kb > kcap || (size_t)kb * b > G.n) return false;
+  {
+    // chol_inv_upper needs the b x b triangle pair in shared memory
+    int dev = 0, max_smem = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (((size_t)b * (b + 1) + b) * sizeof(double) > (size_t)max_smem - 1024) return false;
+  }
+  const int sp = begin_span(SPAN_ORTH);
+  double* Vnew = V.p + (size_t)kold * ldv;
+  auto small_ops = [&](int pass) {  // G.p = Gall (kb x b) -> Z.p = M (kb x b); metrics in small.p[4*pass ..]
+    gemm(stream, true, b, b, kold, 1.0, G.p, kb, G.p, kb, 0.0, S1.p, b, nullptr, 0);  // P = H^T H
+    pip_prepare(stream, kold, b, G.p, S1.p, S2.p, D.p, small.p + 4 * pass);
+    chol_inv_upper(stream, b, S2.p, U.p, small.p + 4 * pass + 3);
+    pip_finish(stream, kold, b, U.p, D.p, Tm.p, Z.p);
+    gemm(stream, false, kold, b, b, -1.0, G.p, kb, Tm.p, b, 0.0, Z.p, kb, nullptr, 0);  // rows 0..k: -H Tm
+  };
+  // pass 1: [V C]^T C in one product, C1 = [V C] M -> T
+  gemm(stream, true, kb, b, nl, 1.0, V.p, ldv, Vnew, ldv, 0.0, G.p, kb, gemm_ws.p, gemm_ws.n);
+  allreduce(G.p, (size_t)kb * b);
+  small_ops(0);
+  gemm(stream, false, nl, b, kb, 1.0, V.p, ldv, Z.p, kb, 0.0, T.p, ldv, nullptr, 0);
+  // pass 2: H = V^T C1, C1^T C1 (two products into one buffer, one all-reduce)
+  gemm(stream, true, kold, b, nl, 1.0, V.p, ldv, T.p, ldv, 0.0, G.p, kb, gemm_ws.p, gemm_ws.n);
+  gemm(stream, true, b, b, nl, 1.0, T.p, ldv, T.p, ldv, 0.0, G.p + kold, kb, gemm_ws.p, gemm_ws.n);
+  allreduce(G.p, (size_t)kb * b);
+  small_ops(1);
+  double h[8];
+  CK(cudaMemcpyAsync(h, small.p, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  // pass 1: pivots safe, Cholesky succeeded; pass 2 started from an almost orthonormal block
+  const bool ok = h[2] == 0.0 && h[3] == 0.0 && h[6] == 0.0 && h[7] == 0.0 && h[4] < 1e-6 && h[5] < 1e-6;
+  if (ok) {
+    // C2 = C1 * Tm - V * (H Tm) -> V(:, kold:)
+    gemm(stream, false, nl, b, b, 1.0, T.p, ldv, Z.p + kold, kb, 0.0, Vnew, ldv, nullptr, 0);
+    gemm(stream, false, nl, b, kold, 1.0, V.p, ldv, Z.p, kb, 1.0, Vnew, ldv, nullptr, 0);
+  }
+  end_span(sp);
+  return ok;
+}
+
 int dav_solver::solve(int lowest, int method, int max_iterations, double tolerance, int max_dim_sub,
                       double* eigenvalues, double* eigenvectors, int64_t ldvec, int* iters) {
   CK(cudaSetDevice(device));
@@ -489,7 +547,12 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
   int kc = std::max(k0, 2 * max_dim);
   if ((int64_t)kc > n) kc = (int)std::max<int64_t>(k0, n);
   alloc_work(L, kc);
-  if (eigenvectors) pinned((size_t)(comm.active() ? n : std::max<int64_t>(nl, 1)) * L);  // outside the timed span
+  if (eigenvectors) {  // staging block for a pageable destination, allocated outside the timed span
+    cudaPointerAttributes pa;
+    const bool direct = cudaPointerGetAttributes(&pa, eigenvectors) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    (void)cudaGetLastError();
+    if (!direct) pinned((size_t)(comm.active() ? n : std::max<int64_t>(nl, 1)) * L);
+  }
 
   std::memset(&stats, 0, sizeof(stats));
   spans.clear();
@@ -555,7 +618,7 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
            ldv, nullptr, 0);
       residual_dpr(stream, nl, nc, R.p + (size_t)c0 * ldv, ldv, C.p + (size_t)c0 * ldv, ldv, theta.p + c0,
                    mat[0].diag.p, gev ? mat[1].diag.p : nullptr, method == DAV_METHOD_DPR, partial.p, norms2.p + c0);
-      allreduce(norms2.p + c0, nc);
+      if (c0 == 0) allreduce(norms2.p, nc);  // only the first L norms are tested (davidson.f90:173-178)
     };
     residual_cols(0, L);
     end_span(sp);
@@ -580,6 +643,7 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
     else converged = std::all_of(has_converged.begin(), has_converged.end(), [](char c) { return c != 0; });
     if (converged || it == max_iterations) {
       // eigenvalues = theta(1:L), eigenvectors = V*Y(:, 1:L) of this Rayleigh-Ritz step (:186-187)
+      const int spo = begin_span(SPAN_OUT);
       gemm(stream, false, nl, L, k, 1.0, V.p, ldv, Y.p, k, 0.0, T.p, ldv, nullptr, 0);
       CK(cudaMemcpyAsync(eigenvalues, theta.p, (size_t)L * 8, cudaMemcpyDeviceToHost, stream));
       int64_t out_rows = 0;
@@ -588,12 +652,23 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
         int64_t ldf = 0;
         const double* Xf = gather_rows(T.p, ldv, L, &ldf);
         out_rows = comm.active() ? n : nl;
-        stage = pinned((size_t)out_rows * L);
-        CK(cudaMemcpy2DAsync(stage, (size_t)out_rows * 8, Xf, (size_t)ldf * 8, (size_t)out_rows * 8, (size_t)L,
-                             cudaMemcpyDeviceToHost, stream));
+        // a page-locked destination (dav_alloc_pinned / cudaHostRegister) is written by DMA directly; a pageable one
+        // goes through the solver's pinned staging block and a host copy
+        cudaPointerAttributes pa;
+        const bool direct = cudaPointerGetAttributes(&pa, eigenvectors) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+        (void)cudaGetLastError();
+        if (direct) {
+          CK(cudaMemcpy2DAsync(eigenvectors, (size_t)ldvec * 8, Xf, (size_t)ldf * 8, (size_t)out_rows * 8, (size_t)L,
+                               cudaMemcpyDeviceToHost, stream));
+        } else {
+          stage = pinned((size_t)out_rows * L);
+          CK(cudaMemcpy2DAsync(stage, (size_t)out_rows * 8, Xf, (size_t)ldf * 8, (size_t)out_rows * 8, (size_t)L,
+                               cudaMemcpyDeviceToHost, stream));
+        }
       }
+      end_span(spo);
       CK(cudaStreamSynchronize(stream));
-      if (eigenvectors) copy_out(stage, out_rows, L, eigenvectors, ldvec);
+      if (stage) copy_out(stage, out_rows, L, eigenvectors, ldvec);
       if (converged) break;
     }
     if (it == max_iterations) { it = max_iterations + 1; break; }
@@ -610,10 +685,16 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
                   (long long)n);
       if (method == DAV_METHOD_GJD) gjd_correction(k, gev);           // C <- GJD corrections
       double* Q = V.p + (size_t)k * ldv;
-      orthonormalize_block(C.p, k, k, Q);                             // steps 6-7 (:210-213)
+      copy_matrix(stream, nl, k, C.p, ldv, Q, ldv);                   // [V | C] contiguous
+      if (!orthonormalize_block_pip(k, k))                            // steps 6-7 (:210-213)
+        orthonormalize_block(Q, k, k, Q);
+      int64_t ldf = 0;
+      const int spg = begin_span(SPAN_GATHER);
+      const double* Qf = gather_rows(Q, ldv, k, &ldf);                // one all-gather for both matrices
+      end_span(spg);
       for (int w = 0; w < (gev ? 2 : 1); ++w) {
         double* W = (w ? BV.p : AV.p) + (size_t)k * ldv;
-        apply(w, Q, ldv, k, W, ldv);                                  // the block matvec
+        apply_full(w, Qf, ldf, k, W, ldv);                            // the block matvec
         project_new_block(w, k, k);
       }
       k *= 2;
@@ -656,6 +737,8 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
       case SPAN_RESID: stats.resid_ms += ms; break;
       case SPAN_PROJ: stats.proj_ms += ms; break;
       case SPAN_INIT: stats.init_ms += ms; break;
+      case SPAN_GATHER: stats.gather_ms += ms; break;
+      case SPAN_OUT: stats.output_ms += ms; break;
       case SPAN_TOTAL: stats.solve_ms = ms; break;
     }
   }

@@ -81,6 +81,7 @@ struct dav_solver {
   void alloc_work(int lowest, int kcap_);
   void rayleigh_ritz(int k, bool gev);
   void orthonormalize_block(double* Cblk, int b, int kold, double* dest);
+  bool orthonormalize_block_pip(int b, int kold);
   void gjd_correction(int k, bool gev);
   void project_new_block(int which, int kold, int b);
   void full_projection(int which, int k);

@@ -115,6 +115,7 @@ class DavidsonSolver:
         return buf.raw
 
     def close(self):
+        self._release_pinned()
         if self._h:
             lib().dav_destroy(self._h)
             self._h = C.c_void_p()
@@ -174,9 +175,33 @@ class DavidsonSolver:
     def set_matvec_impl(self, impl):
         check(lib().dav_set_matvec_impl(self._h, C.c_int(impl)))
 
-    def solve(self, lowest, method, max_iterations, tolerance, max_dim_sub=None, want_vectors=True):
+    def _pinned_vectors(self, n, lowest):
+        """(n x lowest) column-major result array in page-locked memory (reused between solves of one shape):
+        the library then writes the eigenvectors by DMA instead of staging + host copy."""
+        key = (n, lowest)
+        if getattr(self, "_pin_key", None) != key:
+            self._release_pinned()
+            ptr = C.c_void_p()
+            check(lib().dav_alloc_pinned(C.c_size_t(8 * n * lowest), C.byref(ptr)))
+            self._pin_ptr, self._pin_key = ptr, key
+            buf = (C.c_double * (n * lowest)).from_address(ptr.value)
+            self._pin_arr = np.frombuffer(buf, dtype=np.float64).reshape((n, lowest), order="F")
+        return self._pin_arr
+
+    def _release_pinned(self):
+        if getattr(self, "_pin_ptr", None):
+            self._pin_arr = None
+            lib().dav_free_pinned(self._pin_ptr)
+            self._pin_ptr, self._pin_key = None, None
+
+    def solve(self, lowest, method, max_iterations, tolerance, max_dim_sub=None, want_vectors=True, pinned=False):
+        """pinned=True returns the eigenvectors in a page-locked array owned by this handle (valid until the next
+        solve of another shape or close())."""
         ev = np.zeros(lowest)
-        vec = np.zeros((self.n, lowest), order="F") if want_vectors else None
+        if want_vectors:
+            vec = self._pinned_vectors(self.n, lowest) if pinned else np.zeros((self.n, lowest), order="F")
+        else:
+            vec = None
         iters = C.c_int(-1)
         check(lib().dav_solve(self._h, C.c_int(lowest), C.c_int(METHODS[method]), C.c_int(max_iterations),
                               C.c_double(tolerance), C.c_int(max_dim_sub or 0), dp(ev), dp(vec), C.c_int64(self.n),

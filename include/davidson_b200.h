@@ -113,6 +113,11 @@ int dav_create(dav_solver_t** h, int device);
 int dav_create_distributed(dav_solver_t** h, int device, int rank, int world_size, const void* id128);
 int dav_destroy(dav_solver_t* h);
 
+/* page-locked host memory for result arrays: dav_solve / the drop-in calls write eigenvectors into such a block by
+ * DMA directly (a pageable destination is staged and copied on the host instead) */
+int dav_alloc_pinned(size_t bytes, void** ptr);
+int dav_free_pinned(void* ptr);
+
 /* rows [row_begin, row_end) of an n-row matrix owned by `rank` of `world_size` (contiguous blocks,
  * multiples of 128 rows except the last) -- pure host arithmetic, usable without a GPU. */
 int dav_partition_rows(int64_t n, int world_size, int rank, int64_t* row_begin, int64_t* row_end);
@@ -155,6 +160,8 @@ typedef struct {
   double last_matvec_ms;    /* and its kernel time */
   double rr_ms, orth_ms, resid_ms, proj_ms, init_ms; /* phase times (events) */
   int gjd_inner_iterations; /* block-MINRES iterations of the GJD correction (each = one block matvec per matrix) */
+  double gather_ms;         /* all-gather of the new basis block over the ranks (+ staging kernels) */
+  double output_ms;         /* Ritz vectors of the result: V*y, gather, copy to the host */
 } dav_stats_t;
 int dav_get_stats(dav_solver_t* h, dav_stats_t* out);
 

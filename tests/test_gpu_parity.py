@@ -319,6 +319,16 @@ def test_upload_rows_matches_upload():
     s.close()
 
 
+def test_pinned_result_array_matches_pageable():
+    """Eigenvectors written by DMA into a page-locked array (dav_alloc_pinned) == staged copy into a pageable one."""
+    s = fd.DavidsonSolver()
+    s.generate_diagonal_dominant(0, 1200, 1e-2, None, 2)
+    ev1, vec1, it1 = s.solve(4, "DPR", 200, 1e-9)
+    ev2, vec2, it2 = s.solve(4, "DPR", 200, 1e-9, pinned=True)
+    assert it1 == it2 and np.array_equal(ev1, ev2) and np.array_equal(vec1, np.array(vec2))
+    s.close()
+
+
 def test_not_converged_semantics(golden_cases):
     g = golden_cases["notconverged_DPR"]
     A, _ = case_inputs("notconverged_DPR")
