@@ -34,7 +34,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=100000)
+    ap.add_argument("--n", "--size", dest="n", type=int, default=100000)
     ap.add_argument("--lowest", type=int, default=16)
     ap.add_argument("--max-dim", type=int, default=0, help="0 = reference default 10*lowest")
     ap.add_argument("--sparsity", type=float, default=1e-4)
@@ -184,7 +184,9 @@ def workload_config(args, n_gpus):
                             % (args.n, args.lowest, md, args.tol, n_gpus),
                 "n": args.n, "lowest": args.lowest, "method": "DPR", "max_dim_sub": md, "tolerance": args.tol,
                 "l2_policy": "operator entries are generated in shared memory; X block re-read from L2",
-                "parallelism": "row-block x%d" % n_gpus}
+                "result": "eigenvalues on every rank; Ritz vectors row-sharded, each rank its rows (dav_solve_local)"
+                      if n_gpus > 1 else "eigenvalues + Ritz vectors to the host (page-locked array)",
+            "parallelism": "row-block x%d" % n_gpus}
     which = "configs[2]" if (args.n == 100000 and not args.gev) else ("configs[3]" if args.gev else "configs[1]-shape")
     return {"workload": "BASELINE.json %s: dense fp64 generate_diagonal_dominant(n=%d, sparsity=%g, seed 0)%s, "
                         "lowest=%d, %s, max_dim_sub=%d, tol=%g, row-block sharded over %d GPU(s)"
@@ -194,6 +196,8 @@ def workload_config(args, n_gpus):
             "n": args.n, "lowest": args.lowest, "method": args.method, "max_dim_sub": md, "tolerance": args.tol,
             "second_matrix": bool(args.gev),
             "l2_policy": "matrix (%.1f GB) is far larger than L2 (126 MB): no flush needed" % (8e-9 * args.n * args.n),
+            "result": "eigenvalues on every rank; Ritz vectors row-sharded, each rank its rows (dav_solve_local)"
+                      if n_gpus > 1 else "eigenvalues + Ritz vectors to the host (page-locked array)",
             "parallelism": "row-block x%d" % n_gpus}
 
 
@@ -253,7 +257,7 @@ def main():
 
     # ---- warm-up
     for _ in range(args.warmup):
-        ev, _vec, iters = solver.solve(L, args.method, 1000, args.tol, md, want_vectors=True, pinned=True)
+        ev, _vec, iters = solver.solve(L, args.method, 1000, args.tol, md, want_vectors=True, pinned=True, local=distributed)
 
     # ---- timed region: exactly K solves, barrier + synchronize on both sides, device time = CUDA events on the
     # solver's own stream (dav_stats_t.solve_ms), max over ranks
@@ -263,7 +267,7 @@ def main():
     with ClockSampler(local_rank) as clocks:
         w0 = time.perf_counter()
         for _ in range(args.steps):
-            ev, vec, iters = solver.solve(L, args.method, 1000, args.tol, md, want_vectors=True, pinned=True)
+            ev, vec, iters = solver.solve(L, args.method, 1000, args.tol, md, want_vectors=True, pinned=True, local=distributed)
             st = solver.stats()
             dev_ms.append(st.solve_ms)
             mv_ms.append(st.matvec_ms)
@@ -277,8 +281,16 @@ def main():
     value = ms_per_step * 1e-3
 
     # ---- residual check of the result (property at full size): ||A v - lambda v|| <= tol
-    av = solver.block_matvec(0, vec)
     r0, r1 = solver.rows()
+    if distributed:
+        # the timed solves return the Ritz vectors row-sharded (dav_solve_local); assemble them for the check
+        nl_max = max_over_ranks(float(r1 - r0))
+        mine = torch.zeros((int(nl_max), L), dtype=torch.float64, device="cuda")
+        mine[:r1 - r0] = torch.from_numpy(np.ascontiguousarray(vec[:r1 - r0]))
+        parts = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        vec = np.asfortranarray(torch.cat(parts, 0)[:n].cpu().numpy())
+    av = solver.block_matvec(0, vec)
     bv = solver.block_matvec(1, vec) if (args.gev and not args.free) else vec[r0:r1]
     res2 = ((av - bv * ev) ** 2).sum(axis=0)
     if distributed:
@@ -347,7 +359,9 @@ def main():
             "wall_ms_per_step": wall_ms, "generate_s": gen_s,
             "phase_ms": {"matvec": st.matvec_ms, "rayleigh_ritz": st.rr_ms, "orthonormalise": st.orth_ms,
                          "residual_dpr": st.resid_ms, "projection": st.proj_ms, "init": st.init_ms,
-                         "gather_new_block": st.gather_ms, "output_vectors": st.output_ms},
+                         "gather_new_block": st.gather_ms, "output_vectors": st.output_ms,
+                         "nccl_inside_phases": st.comm_ms},
+            "collectives_per_solve": int(st.collectives),
             "gpu_launches": int(sum(launches) / len(launches)), "matvec_launches": int(mv_launch[-1]),
             "clocks": clocks.summary(), "roofline": roofline}
 
@@ -416,7 +430,7 @@ def run_e2e(args, solver, fd, torch, dist, distributed, rank, world, n, L, md, b
         else:
             # sharded: every rank uploads its own row block from its own page-locked host copy
             solver.upload_rows_ptr(0, n, ptr, nl)
-            ev, _v, _it = solver.solve(L, args.method, 1000, args.tol, md, want_vectors=True, pinned=True)
+            ev, _v, _it = solver.solve(L, args.method, 1000, args.tol, md, want_vectors=True, pinned=True, local=distributed)
             solver.clear(0)
         barrier()
         if i > 0:

@@ -18,7 +18,7 @@ SYMBOLS = [
     "dav_create", "dav_create_distributed", "dav_destroy", "dav_alloc_pinned", "dav_free_pinned", "dav_partition_rows",
     "dav_matrix_generate_diagonal_dominant", "dav_matrix_upload", "dav_matrix_upload_rows",
     "dav_matrix_set_operator",
-    "dav_matrix_set_callback", "dav_matrix_clear", "dav_matrix_download", "dav_solve", "dav_get_stats",
+    "dav_matrix_set_callback", "dav_matrix_clear", "dav_matrix_download", "dav_solve", "dav_solve_local", "dav_get_stats",
     "dav_set_matvec_impl", "dav_block_matvec", "dav_bench_block_matvec", "dav_generate_diagonal_dominant",
     "dav_generate_preconditioner", "dav_norm", "dav_lapack_generalized_eigensolver",
     "dav_lapack_generalized_eigensolver_lowest", "dav_sym_eigh_info", "dav_lapack_qr", "dav_lapack_solver", "dav_lapack_matmul",
@@ -34,6 +34,7 @@ class Stats(C.Structure):
         ("last_matvec_b", C.c_int), ("last_matvec_ms", C.c_double), ("rr_ms", C.c_double), ("orth_ms", C.c_double),
         ("resid_ms", C.c_double), ("proj_ms", C.c_double), ("init_ms", C.c_double),
         ("gjd_inner_iterations", C.c_int), ("gather_ms", C.c_double), ("output_ms", C.c_double),
+        ("comm_ms", C.c_double), ("collectives", C.c_int),
     ]
 
 

@@ -238,6 +238,21 @@ int dav_solve(dav_solver_t* h, int lowest, int method, int max_iterations, doubl
   API_END
 }
 
+int dav_solve_local(dav_solver_t* h, int lowest, int method, int max_iterations, double tolerance, int max_dim_sub,
+                    double* eigenvalues, double* eigenvectors_local, int64_t ldv_local, int* iters) {
+  API_BEGIN
+  need(h && eigenvalues && iters, "bad handle / output pointers");
+  h->local_vectors = true;
+  try {
+    h->solve(lowest, method, max_iterations, tolerance, max_dim_sub, eigenvalues, eigenvectors_local, ldv_local, iters);
+  } catch (...) {
+    h->local_vectors = false;
+    throw;
+  }
+  h->local_vectors = false;
+  API_END
+}
+
 int dav_get_stats(dav_solver_t* h, dav_stats_t* out) {
   API_BEGIN
   need(h && out, "bad handle / output");

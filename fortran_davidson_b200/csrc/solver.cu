@@ -31,7 +31,7 @@ using namespace dav;
 
 namespace {
 enum { SPAN_MATVEC = 0, SPAN_RR = 1, SPAN_ORTH = 2, SPAN_RESID = 3, SPAN_PROJ = 4, SPAN_INIT = 5, SPAN_TOTAL = 6,
-       SPAN_GATHER = 7, SPAN_OUT = 8 };
+       SPAN_GATHER = 7, SPAN_OUT = 8, SPAN_COMM = 9 };
 constexpr int EV_POOL = 1024;
 }  // namespace
 
@@ -276,6 +276,21 @@ void dav_solver::end_span(int id) {
   CK(cudaEventRecord(ev_pool[spans[id].b], stream));
 }
 
+void dav_solver::allreduce(double* buf, size_t count) {
+  if (!comm.active()) return;
+  const int sp = begin_span(SPAN_COMM);
+  comm.allreduce_sum(buf, count, stream);
+  end_span(sp);
+  stats.collectives += 1;
+}
+
+void dav_solver::allgather(const void* send, void* recv, size_t bytes_per_rank) {
+  const int sp = begin_span(SPAN_COMM);
+  comm.allgather(send, recv, bytes_per_rank, stream);
+  end_span(sp);
+  stats.collectives += 1;
+}
+
 const double* dav_solver::gather_rows(const double* Xlocal, int64_t ldx, int b, int64_t* ld_out) {
   if (!comm.active()) {
     *ld_out = ldx;
@@ -285,7 +300,7 @@ const double* dav_solver::gather_rows(const double* Xlocal, int64_t ldx, int b, 
   stage_r.alloc((size_t)chunk * b * comm.world());
   Xfull.alloc((size_t)n * b);
   stage_block(stream, Xlocal, ldx, nl, chunk, b, stage_s.p);
-  comm.allgather(stage_s.p, stage_r.p, (size_t)chunk * b * 8, stream);
+  allgather(stage_s.p, stage_r.p, (size_t)chunk * b * 8);
   unstage_allgather(stream, stage_r.p, comm.world(), chunk, n, b, Xfull.p, n);
   *ld_out = n;
   return Xfull.p;
@@ -543,7 +558,9 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
   const int L = lowest, k0 = 2 * L;                                  // davidson.f90:108
   const int max_dim = max_dim_sub > 0 ? max_dim_sub : 10 * L;        // davidson.f90:115-119
   if ((int64_t)k0 > n) DAV_THROW(DAV_ERR_INVALID, "2*lowest = %d exceeds the matrix dimension %lld", k0, (long long)n);
-  if (eigenvectors && ldvec < n) DAV_THROW(DAV_ERR_INVALID, "eigenvector leading dimension too small");
+  const bool gather_out = comm.active() && !local_vectors;
+  if (eigenvectors && ldvec < (gather_out || !comm.active() ? n : std::max<int64_t>(nl, 1)))
+    DAV_THROW(DAV_ERR_INVALID, "eigenvector leading dimension too small");
   int kc = std::max(k0, 2 * max_dim);
   if ((int64_t)kc > n) kc = (int)std::max<int64_t>(k0, n);
   alloc_work(L, kc);
@@ -551,7 +568,7 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
     cudaPointerAttributes pa;
     const bool direct = cudaPointerGetAttributes(&pa, eigenvectors) == cudaSuccess && pa.type == cudaMemoryTypeHost;
     (void)cudaGetLastError();
-    if (!direct) pinned((size_t)(comm.active() ? n : std::max<int64_t>(nl, 1)) * L);
+    if (!direct) pinned((size_t)(gather_out ? n : std::max<int64_t>(nl, 1)) * L);
   }
 
   std::memset(&stats, 0, sizeof(stats));
@@ -571,8 +588,8 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
     const int P = comm.world();
     double* allv = cand_val.p + k0;
     int64_t* alli = cand_idx.p + k0;
-    comm.allgather(cand_val.p, allv, (size_t)k0 * 8, stream);
-    comm.allgather(cand_idx.p, alli, (size_t)k0 * 8, stream);
+    allgather(cand_val.p, allv, (size_t)k0 * 8);
+    allgather(cand_idx.p, alli, (size_t)k0 * 8);
     topk_smallest(stream, allv, alli, (int64_t)k0 * P, 0, k0, cand_val.p, idx.p, status.p, topk_val.p, topk_idx.p);
   } else {
     CK(cudaMemcpyAsync(idx.p, cand_idx.p, (size_t)k0 * 8, cudaMemcpyDeviceToDevice, stream));
@@ -649,9 +666,9 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
       int64_t out_rows = 0;
       double* stage = nullptr;
       if (eigenvectors) {
-        int64_t ldf = 0;
-        const double* Xf = gather_rows(T.p, ldv, L, &ldf);
-        out_rows = comm.active() ? n : nl;
+        int64_t ldf = ldv;
+        const double* Xf = gather_out ? gather_rows(T.p, ldv, L, &ldf) : T.p;
+        out_rows = gather_out ? n : nl;
         // a page-locked destination (dav_alloc_pinned / cudaHostRegister) is written by DMA directly; a pageable one
         // goes through the solver's pinned staging block and a host copy
         cudaPointerAttributes pa;
@@ -739,6 +756,7 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
       case SPAN_INIT: stats.init_ms += ms; break;
       case SPAN_GATHER: stats.gather_ms += ms; break;
       case SPAN_OUT: stats.output_ms += ms; break;
+      case SPAN_COMM: stats.comm_ms += ms; break;
       case SPAN_TOTAL: stats.solve_ms = ms; break;
     }
   }

@@ -30,6 +30,7 @@ struct dav_solver {
   dav::DevBuf<double> etab;  // e_t table of the built-in operators
   std::vector<double> etab_host;
   int matvec_impl = DAV_MATVEC_AUTO;
+  bool local_vectors = false;  // dav_solve_local: Ritz vectors returned row-sharded
   dav_stats_t stats;
 
   // ---- work space of a solve
@@ -85,7 +86,8 @@ struct dav_solver {
   void gjd_correction(int k, bool gev);
   void project_new_block(int which, int kold, int b);
   void full_projection(int which, int k);
-  void allreduce(double* buf, size_t count) { comm.allreduce_sum(buf, count, stream); }
+  void allreduce(double* buf, size_t count);
+  void allgather(const void* send, void* recv, size_t bytes_per_rank);
   int begin_span(int kind);
   void end_span(int id);
   void check_status(const char* where);

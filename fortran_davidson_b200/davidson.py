@@ -194,14 +194,26 @@ class DavidsonSolver:
             lib().dav_free_pinned(self._pin_ptr)
             self._pin_ptr, self._pin_key = None, None
 
-    def solve(self, lowest, method, max_iterations, tolerance, max_dim_sub=None, want_vectors=True, pinned=False):
+    def solve(self, lowest, method, max_iterations, tolerance, max_dim_sub=None, want_vectors=True, pinned=False,
+              local=False):
         """pinned=True returns the eigenvectors in a page-locked array owned by this handle (valid until the next
-        solve of another shape or close())."""
+        solve of another shape or close()).  local=True (dav_solve_local): every rank gets only its rows() of the
+        Ritz vectors instead of the all-gathered block."""
         ev = np.zeros(lowest)
+        rows = self.n
+        if local:
+            r0, r1 = self.rows()
+            rows = max(r1 - r0, 1)
         if want_vectors:
-            vec = self._pinned_vectors(self.n, lowest) if pinned else np.zeros((self.n, lowest), order="F")
+            vec = self._pinned_vectors(rows, lowest) if pinned else np.zeros((rows, lowest), order="F")
         else:
             vec = None
+        if local:
+            iters = C.c_int(-1)
+            check(lib().dav_solve_local(self._h, C.c_int(lowest), C.c_int(METHODS[method]), C.c_int(max_iterations),
+                                        C.c_double(tolerance), C.c_int(max_dim_sub or 0), dp(ev), dp(vec),
+                                        C.c_int64(rows), C.byref(iters)))
+            return ev, vec, (iters.value if iters.value >= 0 else None)
         iters = C.c_int(-1)
         check(lib().dav_solve(self._h, C.c_int(lowest), C.c_int(METHODS[method]), C.c_int(max_iterations),
                               C.c_double(tolerance), C.c_int(max_dim_sub or 0), dp(ev), dp(vec), C.c_int64(self.n),

@@ -144,6 +144,11 @@ int dav_matrix_download(dav_solver_t* h, int which, double* host_rows, int64_t l
  * eigenvectors: full n x lowest on every rank (may be NULL to skip the device->host copy). */
 int dav_solve(dav_solver_t* h, int lowest, int method, int max_iterations, double tolerance, int max_dim_sub,
               double* eigenvalues, double* eigenvectors, int64_t ldv, int* iters);
+/* row-sharded result: like dav_solve, but every rank receives only ITS rows of the Ritz vectors
+ * (rows dav_partition_rows(n, world, rank) x lowest, leading dimension ldv_local) -- no all-gather of the result.
+ * On a single-rank handle it is identical to dav_solve. */
+int dav_solve_local(dav_solver_t* h, int lowest, int method, int max_iterations, double tolerance, int max_dim_sub,
+                    double* eigenvalues, double* eigenvectors_local, int64_t ldv_local, int* iters);
 
 typedef struct {
   double solve_ms;          /* CUDA-event time of the last dav_solve (device work of the whole loop) */
@@ -162,6 +167,8 @@ typedef struct {
   int gjd_inner_iterations; /* block-MINRES iterations of the GJD correction (each = one block matvec per matrix) */
   double gather_ms;         /* all-gather of the new basis block over the ranks (+ staging kernels) */
   double output_ms;         /* Ritz vectors of the result: V*y, gather, copy to the host */
+  double comm_ms;           /* time inside NCCL collectives (nested in the phases above; includes waiting for peers) */
+  int collectives;          /* NCCL calls of the solve */
 } dav_stats_t;
 int dav_get_stats(dav_solver_t* h, dav_stats_t* out);
 

@@ -42,6 +42,8 @@ def main():
             assert np.abs(sg * vec[:, j] - r.eigenvectors[:, j]).max() < 1e-8
             assert np.linalg.norm(A @ vec[:, j] - ev[j] * (Bm @ vec[:, j])) < max(tol, 1e-8)
         r0, r1 = s.rows()
+        evl, vecl, itl = s.solve(L, method, 200, tol, md, local=True)   # row-sharded result
+        assert itl == iters and np.array_equal(evl, ev) and np.array_equal(vecl[:r1 - r0], vec[r0:r1])
         blk = s.download(0)
         assert np.array_equal(blk, A[r0:r1])
         if rank == 0:
