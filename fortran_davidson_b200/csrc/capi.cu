@@ -148,6 +148,13 @@ int dav_partition_rows(int64_t n, int world_size, int rank, int64_t* row_begin, 
   return DAV_OK;
 }
 
+int dav_debug_matvec_schedule(int64_t m, int64_t k, int b, int num_sms, int schedule, long long* info) {
+  API_BEGIN
+  const int rc = matvec_schedule_selftest(m, k, b, num_sms, schedule, info);
+  if (rc != 0) DAV_THROW(DAV_ERR_INVALID, "matvec schedule self-test failed: check %d", rc);
+  API_END
+}
+
 // ---------------------------------------------------------------------------------------------
 // handle API
 // ---------------------------------------------------------------------------------------------

@@ -24,6 +24,8 @@ void matvec_plan_destroy(MatvecPlan* p);
 bool matvec_dmma_supported();
 // X is K x b column-major (ldx); Xp is scratch for the packed copy of X (>= round_up(K,64)*round_up(b,8)).
 void matvec_dmma(cudaStream_t s, MatvecPlan* plan, int b, const double* X, int64_t ldx, double* W, int64_t ldw);
+// host model of the (waves + stream-K) schedule the kernel executes; see matvec_dmma.cu.  0 = consistent.
+int matvec_schedule_selftest(int64_t M, int64_t K, int b, int num_sms, int schedule, long long* info);
 
 // ---- freeops.cu : on-the-fly operators (benchmark_free.f90:38-76, tests/test_utils.f90:37-116) --
 // W(rows row0..row0+nl) = Op * X(n x b); etab[n] = (double)expf(i/n) table (built on host with glibc expf).

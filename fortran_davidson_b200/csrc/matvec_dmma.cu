@@ -4,9 +4,13 @@
 // iteration (davidson.f90:163-170).
 //
 // sm_100a design
-//   * persistent grid, one CTA per SM, stream-K: the (row tile x k step) units are split evenly and
-//     contiguously over the CTAs; partially covered tiles go to a workspace and a tiny fixup kernel
-//     adds them in a fixed order (bit-reproducible, no atomics).
+//   * persistent grid, one CTA per SM.  Schedule = full WAVES + a stream-K remainder: while at least `grid` row
+//     tiles are left, CTA c takes tile (wave*grid + c) and all CTAs sweep the k steps together, so at any moment
+//     the whole grid reads the same ~16 columns of A (contiguous in HBM over the row tiles, the same few 2 MB
+//     pages for every SM, one X tile shared through L2).  The tiles that do not fill a wave are split stream-K:
+//     their (row tile x k step) units are divided evenly and contiguously over the CTAs; partially covered tiles
+//     go to a workspace and a tiny fixup kernel adds them in a fixed order (bit-reproducible, no atomics).
+//     DAV_MATVEC_SCHEDULE=0 selects pure stream-K (every CTA at a different k position).
 //   * warp-specialised: warp 8 is the TMA producer, warps 0-7 consume (each 32 rows x up to 32 columns).  A tiles arrive through a
 //     2D tensor map (box 16 rows x 16 columns, 128-byte swizzle) with mbarrier complete_tx; the X
 //     tile is pre-packed in fragment order so one 1D bulk copy per stage fetches it.
@@ -34,6 +38,7 @@ constexpr int CONSUMERS = 8;      // consumer warps
 constexpr int THREADS = (CONSUMERS + 1) * 32;
 constexpr int MAX_STAGES = 8;
 constexpr int NUM_SMS_FALLBACK = 148;
+constexpr int MATVEC_SCHEDULE_DEFAULT = 0;  // see the header comment; DAV_MATVEC_SCHEDULE overrides
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -111,12 +116,85 @@ __device__ __forceinline__ double2 lds128(uint32_t addr) {
   return v;
 }
 
+// ---- the schedule: shared by the kernel, the fixup kernel and the host self-test (dav_debug_matvec_schedule) ----
+#define DAV_HD __host__ __device__ __forceinline__
+struct Sched {
+  int tiles, ksteps;   // row tiles, k steps
+  int grid;            // CTAs launched
+  int waves;           // full waves: CTA c owns the tiles w*grid + c, w < waves, completely
+  int tile_off;        // first tile of the stream-K remainder (= waves * grid)
+  long long total;     // (tiles - tile_off) * ksteps: units of the stream-K remainder
+  long long quota;     // remainder units per CTA (0 when there is no remainder)
+};
+// consecutive k steps [ks0, ks1) of one row tile; slot < 0: the whole tile (written to W directly), else the
+// workspace slot of the CTA that receives the partial sums
+struct Segment {
+  int tile, ks0, ks1, slot;
+};
+struct SegCursor {
+  int wave;
+  long long u, u_begin, u_end;
+};
+DAV_HD SegCursor seg_begin(const Sched& sc, int cta) {
+  SegCursor c;
+  c.wave = 0;
+  const long long ub = (long long)cta * sc.quota;
+  c.u_begin = ub < sc.total ? ub : sc.total;
+  const long long ue = c.u_begin + sc.quota;
+  c.u_end = ue < sc.total ? ue : sc.total;
+  c.u = c.u_begin;
+  return c;
+}
+DAV_HD bool seg_next(const Sched& sc, int cta, SegCursor& c, Segment& sg) {
+  if (c.wave < sc.waves) {
+    sg.tile = c.wave * sc.grid + cta;
+    sg.ks0 = 0;
+    sg.ks1 = sc.ksteps;
+    sg.slot = -1;
+    ++c.wave;
+    return true;
+  }
+  if (c.u >= c.u_end) return false;
+  const int rt = (int)(c.u / sc.ksteps);
+  sg.tile = sc.tile_off + rt;
+  sg.ks0 = (int)(c.u - (long long)rt * sc.ksteps);
+  const long long left = c.u_end - c.u;
+  sg.ks1 = (long long)sg.ks0 + left < (long long)sc.ksteps ? (int)(sg.ks0 + left) : sc.ksteps;
+  const bool complete = sg.ks0 == 0 && sg.ks1 == sc.ksteps;
+  sg.slot = complete ? -1 : (c.u == c.u_begin ? 0 : 1);  // a CTA has at most a first and a last partial segment
+  c.u += sg.ks1 - sg.ks0;
+  return true;
+}
+// CTAs [cA, cB] hold the pieces of remainder tile rt (cA == cB: written directly); piece of CTA c is in fixup_slot
+DAV_HD void fixup_range(const Sched& sc, int rt, int& cA, int& cB) {
+  const long long u0 = (long long)rt * sc.ksteps, u1 = u0 + sc.ksteps;
+  cA = (int)(u0 / sc.quota);
+  cB = (int)((u1 - 1) / sc.quota);
+}
+DAV_HD int fixup_slot(const Sched& sc, int c, int rt) {
+  return ((long long)c * sc.quota >= (long long)rt * sc.ksteps) ? 0 : 1;
+}
+// schedule != 0: full waves first (all CTAs on the same k step), the tiles that do not fill a wave as stream-K;
+// schedule == 0: everything stream-K.  max_grid: SM count, already limited by the workspace (2 slots per CTA).
+inline Sched make_sched(int tiles, int ksteps, int max_grid, int schedule) {
+  Sched sc;
+  sc.tiles = tiles;
+  sc.ksteps = ksteps;
+  const long long all_units = (long long)tiles * ksteps;
+  int grid = (int)std::min<long long>(std::max(max_grid, 1), std::max<long long>(all_units, 1));
+  sc.waves = (schedule != 0 && tiles >= grid) ? tiles / grid : 0;
+  sc.tile_off = sc.waves * grid;
+  sc.total = (long long)(tiles - sc.tile_off) * ksteps;
+  sc.quota = sc.total > 0 ? (sc.total + grid - 1) / grid : 0;
+  if (sc.waves == 0 && sc.quota > 0) grid = (int)((sc.total + sc.quota - 1) / sc.quota);
+  sc.grid = grid;
+  return sc;
+}
+
 struct Params {
   int64_t M, K;        // rows of the local block, columns (= global n)
   int b;               // real column count (<= bpad)
-  int tiles, ksteps;   // row tiles, k steps
-  long long total;     // tiles * ksteps
-  long long quota;     // units per CTA
+  Sched sc;
   int stages;
   int l2_hints;        // bit 0: evict_first on the A stream, bit 1: evict_last on the packed X block
   const double* Xp;    // packed X: [kstep][BK x bpad] in fragment order
@@ -171,20 +249,19 @@ __global__ void __launch_bounds__(THREADS, 1)
   }
   __syncthreads();
 
-  const long long u_begin = (long long)blockIdx.x * p.quota;
-  const long long u_end = min(p.total, u_begin + p.quota);
-  if (u_begin >= u_end) return;
+  const Sched& sc = p.sc;
+  SegCursor cur = seg_begin(sc, (int)blockIdx.x);
+  Segment sg;
 
   if (warp == CONSUMERS) {
     // ================= TMA producer (one elected lane) =================
     if (lane == 0) {
       long long it = 0;
       const uint64_t pol_a = policy_evict_first(), pol_x = policy_evict_last();
-      for (long long u = u_begin; u < u_end; ++u, ++it) {
+      auto load_stage = [&](int tile, int ks) {
         const int s = (int)(it % S);
         const uint32_t ph = (uint32_t)((it / S) & 1);
         mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
-        const int tile = (int)(u / p.ksteps), ks = (int)(u % p.ksteps);
         const uint32_t fb = smem_u32(&full_bar[s]);
         mbar_expect_tx(fb, STAGE_BYTES);
         const uint32_t a_dst = base + (uint32_t)s * STAGE_BYTES;
@@ -201,7 +278,10 @@ __global__ void __launch_bounds__(THREADS, 1)
           bulk_load_1d(a_dst + A_BYTES, p.Xp + (size_t)ks * (BK * BPAD), X_BYTES, fb, pol_x);
         else
           bulk_load_1d_nohint(a_dst + A_BYTES, p.Xp + (size_t)ks * (BK * BPAD), X_BYTES, fb);
-      }
+        ++it;
+      };
+      while (seg_next(sc, (int)blockIdx.x, cur, sg))
+        for (int ks = sg.ks0; ks < sg.ks1; ++ks) load_stage(sg.tile, ks);
     }
     return;
   }
@@ -218,12 +298,8 @@ __global__ void __launch_bounds__(THREADS, 1)
   const uint32_t x_lane = A_BYTES + (uint32_t)((wc * NT) * 64 + g * 8 + 2 * t) * 8;
 
   long long it = 0;
-  long long u = u_begin;
-  while (u < u_end) {
-    // one segment = consecutive k steps of one row tile
-    const int tile = (int)(u / p.ksteps);
-    const int ks0 = (int)(u - (long long)tile * p.ksteps);
-    const int ks1 = (int)min((long long)p.ksteps, (long long)ks0 + (u_end - u));
+  while (seg_next(sc, (int)blockIdx.x, cur, sg)) {
+    const int tile = sg.tile, ks0 = sg.ks0, ks1 = sg.ks1;
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -261,8 +337,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       if (lane == 0) mbar_arrive(smem_u32(&empty_bar[s]));
     }
 
-    const bool complete = (ks0 == 0) && (ks1 == p.ksteps);
-    if (complete) {
+    if (sg.slot < 0) {
       const int64_t row_base = (int64_t)tile * BM + wr * 32;
 #pragma unroll
       for (int rg = 0; rg < 2; ++rg)
@@ -279,9 +354,8 @@ __global__ void __launch_bounds__(THREADS, 1)
           }
         }
     } else {
-      // partial tile -> workspace slot (0: the CTA's first segment, 1: a later one)
-      const int slot = (u == u_begin) ? 0 : 1;
-      double* w = p.ws + ((size_t)blockIdx.x * 2 + slot) * (size_t)(BM * BPAD);
+      // partial tile -> workspace slot (0: the CTA's first segment, 1: its last one)
+      double* w = p.ws + ((size_t)blockIdx.x * 2 + sg.slot) * (size_t)(BM * BPAD);
 #pragma unroll
       for (int rg = 0; rg < 2; ++rg)
 #pragma unroll
@@ -295,15 +369,15 @@ __global__ void __launch_bounds__(THREADS, 1)
           }
         }
     }
-    u += ks1 - ks0;
   }
 }
 
 // Adds the partial tiles of every row tile that was split over several CTAs, in CTA order.
 __global__ void fixup_kernel(int BM, int BPAD, Params p) {
-  const int tile = blockIdx.x;
-  const long long u0 = (long long)tile * p.ksteps, u1 = u0 + p.ksteps;
-  const int cA = (int)(u0 / p.quota), cB = (int)((u1 - 1) / p.quota);
+  const int rt = blockIdx.x;  // tile of the stream-K remainder
+  const int tile = p.sc.tile_off + rt;
+  int cA, cB;
+  fixup_range(p.sc, rt, cA, cB);
   if (cA == cB) return;  // written directly
   const int elems = BM * BPAD;
   for (int e = threadIdx.x; e < elems; e += blockDim.x) {
@@ -311,10 +385,7 @@ __global__ void fixup_kernel(int BM, int BPAD, Params p) {
     const int64_t row = (int64_t)tile * BM + r;
     if (row >= p.M || j >= p.b) continue;
     double s = 0.0;
-    for (int c = cA; c <= cB; ++c) {
-      const int slot = ((long long)c * p.quota >= u0) ? 0 : 1;
-      s += p.ws[((size_t)c * 2 + slot) * (size_t)elems + e];
-    }
+    for (int c = cA; c <= cB; ++c) s += p.ws[((size_t)c * 2 + fixup_slot(p.sc, c, rt)) * (size_t)elems + e];
     p.W[row + (int64_t)j * p.ldw] = s;
   }
 }
@@ -340,18 +411,16 @@ EncodeTiledFn get_encode_fn() {
 }
 
 template <int NT, int WARPS_N>
-void launch_cfg(cudaStream_t s, const CUtensorMap& map, Params& p, int max_smem, int num_sms, double* ws,
-                size_t ws_doubles) {
+void launch_cfg(cudaStream_t s, const CUtensorMap& map, Params& p, int ksteps, int max_smem, int num_sms, double* ws,
+                size_t ws_doubles, int schedule) {
   constexpr int BM = (CONSUMERS / WARPS_N) * 32;
   constexpr int BPAD = NT * WARPS_N * 8;
   constexpr int STAGE_BYTES = BM * BK * 8 + BK * BPAD * 8;
-  p.tiles = (int)ceil_div(p.M, BM);
-  p.total = (long long)p.tiles * p.ksteps;
-  int grid = (int)std::min<long long>(num_sms, p.total);
   const size_t slot = (size_t)BM * BPAD;
-  if ((size_t)grid * 2 * slot > ws_doubles) grid = (int)std::max<size_t>(1, ws_doubles / (2 * slot));
-  p.quota = (p.total + grid - 1) / grid;
-  grid = (int)((p.total + p.quota - 1) / p.quota);
+  const int max_grid = (int)std::min<size_t>((size_t)num_sms, std::max<size_t>(1, ws_doubles / (2 * slot)));
+  p.sc = make_sched((int)ceil_div(p.M, BM), ksteps, max_grid, schedule);
+  const int grid = p.sc.grid;
+  const int rem_tiles = p.sc.tiles - p.sc.tile_off;
   p.stages = std::min(MAX_STAGES, (max_smem - 1024 - 256) / STAGE_BYTES);
   if (p.stages < 2) DAV_THROW(DAV_ERR_CUDA, "not enough shared memory for the matvec pipeline");
   p.ws = ws;
@@ -364,12 +433,92 @@ void launch_cfg(cudaStream_t s, const CUtensorMap& map, Params& p, int max_smem,
   matvec_kernel<NT, WARPS_N><<<grid, THREADS, smem, s>>>(map, p);
   CK_LAUNCH();
   ++g_kernel_launches;
-  fixup_kernel<<<p.tiles, 256, 0, s>>>(BM, BPAD, p);
-  CK_LAUNCH();
-  ++g_kernel_launches;
+  if (rem_tiles > 0) {
+    fixup_kernel<<<rem_tiles, 256, 0, s>>>(BM, BPAD, p);
+    CK_LAUNCH();
+    ++g_kernel_launches;
+  }
 }
 
 }  // namespace
+
+// config: 8 consumer warps as (8/WN row warps) x (WN column warps); a warp owns 32 rows x NT*8 columns with
+// NT <= 4 (the 9-warp CTA is granted at most 168 registers per thread)
+//   bpad <= 32 : WN=1, BM=256   | bpad <= 64 : WN=2, BM=128   | bpad <= 128 : WN=4, BM=64
+static void pick_cfg(int bc, int* warps_n, int* nt, int* bpad) {
+  int bp = (int)round_up(bc, 8);
+  *warps_n = bp <= 32 ? 1 : (bp <= 64 ? 2 : 4);
+  *nt = (bp + 8 * *warps_n - 1) / (8 * *warps_n);
+  if (*warps_n > 1 && *nt < 3) *nt = 3;  // instantiated tile shapes: NT 1..4 for WN=1, NT 3..4 for WN=2,4
+  *bpad = *nt * *warps_n * 8;
+}
+
+static int schedule_from_env() {
+  // 1: full waves + stream-K remainder; 0: pure stream-K.  Read per call so one process can compare the two.
+  const char* e = std::getenv("DAV_MATVEC_SCHEDULE");
+  return e ? std::atoi(e) : MATVEC_SCHEDULE_DEFAULT;
+}
+
+// Host model of the schedule the kernels execute (same inline functions): enumerates the segments of every CTA and
+// checks that each (row tile, k step) unit is covered exactly once, that a CTA uses each workspace slot at most
+// once, and that the fixup kernel reads exactly the partial segments of each remainder tile.  No device needed.
+// info[8] = {grid, waves, tile_off, quota, tiles, ksteps, partial segments, BM}.  Returns 0 when consistent.
+int matvec_schedule_selftest(int64_t M, int64_t K, int b, int num_sms, int schedule, long long* info) {
+  if (M <= 0 || K <= 0 || b <= 0 || b > 128 || num_sms <= 0) return -1;
+  int warps_n, nt, bpad;
+  pick_cfg(b, &warps_n, &nt, &bpad);
+  const int BM = (CONSUMERS / warps_n) * 32;
+  const int tiles = (int)ceil_div(M, (int64_t)BM);
+  const int ksteps = (int)(round_up(K, BK) / BK);
+  if (schedule < 0) schedule = schedule_from_env();
+  const Sched sc = make_sched(tiles, ksteps, num_sms, schedule);
+  if (sc.grid < 1 || sc.grid > num_sms) return 1;
+  if ((long long)tiles * ksteps > (1LL << 28)) return -2;  // the coverage map below is meant for test sizes
+  std::vector<unsigned char> cover((size_t)tiles * ksteps, 0);
+  // partial pieces per remainder tile: (cta, slot, ks0, ks1)
+  struct Piece { int cta, slot, ks0, ks1; };
+  std::vector<std::vector<Piece>> pieces((size_t)(tiles - sc.tile_off));
+  long long npartial = 0;
+  for (int c = 0; c < sc.grid; ++c) {
+    SegCursor cur = seg_begin(sc, c);
+    Segment sg;
+    int slot_used[2] = {0, 0};
+    while (seg_next(sc, c, cur, sg)) {
+      if (sg.tile < 0 || sg.tile >= tiles || sg.ks0 < 0 || sg.ks1 > ksteps || sg.ks0 >= sg.ks1) return 2;
+      for (int ks = sg.ks0; ks < sg.ks1; ++ks)
+        if (cover[(size_t)sg.tile * ksteps + ks]++) return 3;  // covered twice
+      const bool complete = sg.ks0 == 0 && sg.ks1 == ksteps;
+      if (complete != (sg.slot < 0)) return 4;
+      if (!complete) {
+        if (sg.tile < sc.tile_off) return 5;  // a wave tile must be complete
+        if (sg.slot > 1 || slot_used[sg.slot]++) return 6;
+        pieces[(size_t)(sg.tile - sc.tile_off)].push_back(Piece{c, sg.slot, sg.ks0, sg.ks1});
+        ++npartial;
+      }
+    }
+  }
+  for (unsigned char v : cover)
+    if (v != 1) return 7;  // not covered
+  for (int rt = 0; rt < tiles - sc.tile_off; ++rt) {
+    int cA, cB;
+    fixup_range(sc, rt, cA, cB);
+    const std::vector<Piece>& pc = pieces[(size_t)rt];
+    if (cA == cB) {
+      if (!pc.empty()) return 8;  // fixup would skip a tile that has partial pieces
+      continue;
+    }
+    if ((int)pc.size() != cB - cA + 1) return 9;
+    for (int c = cA; c <= cB; ++c) {
+      const Piece& q = pc[(size_t)(c - cA)];  // CTAs were enumerated in order
+      if (q.cta != c || q.slot != fixup_slot(sc, c, rt)) return 10;
+    }
+  }
+  if (info) {
+    info[0] = sc.grid; info[1] = sc.waves; info[2] = sc.tile_off; info[3] = sc.quota;
+    info[4] = tiles; info[5] = ksteps; info[6] = npartial; info[7] = BM;
+  }
+  return 0;
+}
 
 struct MatvecPlan {
   CUtensorMap map;
@@ -418,13 +567,8 @@ void matvec_dmma(cudaStream_t s, MatvecPlan* plan, int b, const double* X, int64
   const int64_t Kpad = round_up(plan->K, BK);
   for (int j0 = 0; j0 < b; j0 += 128) {
     const int bc = std::min(128, b - j0);
-    int bpad = (int)round_up(bc, 8);
-    // config: 8 consumer warps as (8/WN row warps) x (WN column warps); a warp owns 32 rows x NT*8 columns with
-    // NT <= 4 (the 9-warp CTA is granted at most 168 registers per thread)
-    //   bpad <= 32 : WN=1, BM=256   | bpad <= 64 : WN=2, BM=128   | bpad <= 128 : WN=4, BM=64
-    int warps_n = bpad <= 32 ? 1 : (bpad <= 64 ? 2 : 4);
-    int nt = (bpad + 8 * warps_n - 1) / (8 * warps_n);
-    bpad = nt * warps_n * 8;
+    int warps_n, nt, bpad;
+    pick_cfg(bc, &warps_n, &nt, &bpad);
     if ((size_t)Kpad * bpad > plan->Xp.n) plan->Xp.alloc((size_t)Kpad * bpad);
     {
       const int64_t total = Kpad * bpad;
@@ -435,7 +579,7 @@ void matvec_dmma(cudaStream_t s, MatvecPlan* plan, int b, const double* X, int64
     }
     Params p;
     p.M = plan->M; p.K = plan->K; p.b = bc;
-    p.ksteps = (int)(Kpad / BK);
+    const int ksteps = (int)(Kpad / BK);
     p.Xp = plan->Xp.p;
     p.W = W + (int64_t)j0 * ldw;
     p.ldw = ldw;
@@ -443,8 +587,9 @@ void matvec_dmma(cudaStream_t s, MatvecPlan* plan, int b, const double* X, int64
       static const int hints = [] { const char* e = std::getenv("DAV_MATVEC_L2_HINTS"); return e ? std::atoi(e) : 2; }();
       p.l2_hints = hints;
     }
+    const int schedule = schedule_from_env();
 #define CFG(NT_, WN_)                                                                                      \
-  launch_cfg<NT_, WN_>(s, plan->map, p, plan->max_smem, plan->num_sms, plan->ws.p, plan->ws.n)
+  launch_cfg<NT_, WN_>(s, plan->map, p, ksteps, plan->max_smem, plan->num_sms, plan->ws.p, plan->ws.n, schedule)
     if (warps_n == 1) {
       switch (nt) {
         case 1: CFG(1, 1); break;
