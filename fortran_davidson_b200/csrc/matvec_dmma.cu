@@ -118,13 +118,20 @@ __device__ __forceinline__ double2 lds128(uint32_t addr) {
 
 // ---- the schedule: shared by the kernel, the fixup kernel and the host self-test (dav_debug_matvec_schedule) ----
 #define DAV_HD __host__ __device__ __forceinline__
+constexpr int WS_SLOTS = 4;  // workspace slots (partial tiles) per CTA
 struct Sched {
   int tiles, ksteps;   // row tiles, k steps
   int grid;            // CTAs launched
   int waves;           // full waves: CTA c owns the tiles w*grid + c, w < waves, completely
-  int tile_off;        // first tile of the stream-K remainder (= waves * grid)
-  long long total;     // (tiles - tile_off) * ksteps: units of the stream-K remainder
-  long long quota;     // remainder units per CTA (0 when there is no remainder)
+  int tile_off;        // first tile of the remainder (= waves * grid)
+  int rem_tiles;       // tiles - tile_off
+  // remainder, variant A (split == 0), stream-K: the rem_tiles * ksteps units are cut into `grid` contiguous ranges
+  long long total;     // rem_tiles * ksteps
+  long long quota;     // units per CTA (0 when there is no remainder)
+  // remainder, variant B (split >= 1), aligned split-K: every remainder tile is cut into `split` pieces of kchunk
+  // k steps; piece v = j * rem_tiles + rt (j-major) goes to CTA v % grid as its (v / grid)-th remainder segment, so
+  // the CTAs of one round sit on at most a few distinct k positions
+  int split, kchunk;
 };
 // consecutive k steps [ks0, ks1) of one row tile; slot < 0: the whole tile (written to W directly), else the
 // workspace slot of the CTA that receives the partial sums
@@ -132,12 +139,13 @@ struct Segment {
   int tile, ks0, ks1, slot;
 };
 struct SegCursor {
-  int wave;
+  int wave, round;
   long long u, u_begin, u_end;
 };
 DAV_HD SegCursor seg_begin(const Sched& sc, int cta) {
   SegCursor c;
   c.wave = 0;
+  c.round = 0;
   const long long ub = (long long)cta * sc.quota;
   c.u_begin = ub < sc.total ? ub : sc.total;
   const long long ue = c.u_begin + sc.quota;
@@ -154,6 +162,17 @@ DAV_HD bool seg_next(const Sched& sc, int cta, SegCursor& c, Segment& sg) {
     ++c.wave;
     return true;
   }
+  if (sc.split > 0) {
+    const long long v = (long long)c.round * sc.grid + cta;
+    if (v >= (long long)sc.rem_tiles * sc.split) return false;
+    const int j = (int)(v / sc.rem_tiles), rt = (int)(v - (long long)j * sc.rem_tiles);
+    sg.tile = sc.tile_off + rt;
+    sg.ks0 = j * sc.kchunk;
+    sg.ks1 = sg.ks0 + sc.kchunk < sc.ksteps ? sg.ks0 + sc.kchunk : sc.ksteps;
+    sg.slot = sc.split == 1 ? -1 : c.round;
+    ++c.round;
+    return true;
+  }
   if (c.u >= c.u_end) return false;
   const int rt = (int)(c.u / sc.ksteps);
   sg.tile = sc.tile_off + rt;
@@ -165,17 +184,28 @@ DAV_HD bool seg_next(const Sched& sc, int cta, SegCursor& c, Segment& sg) {
   c.u += sg.ks1 - sg.ks0;
   return true;
 }
-// CTAs [cA, cB] hold the pieces of remainder tile rt (cA == cB: written directly); piece of CTA c is in fixup_slot
-DAV_HD void fixup_range(const Sched& sc, int rt, int& cA, int& cB) {
+// The fixup pass adds the fixup_count(rt) partial pieces of remainder tile rt in increasing-k order (0: the tile was
+// written directly); piece i sits in workspace slot `slot` of CTA `cta`.
+DAV_HD int fixup_count(const Sched& sc, int rt) {
+  if (sc.split > 0) return sc.split == 1 ? 0 : sc.split;
   const long long u0 = (long long)rt * sc.ksteps, u1 = u0 + sc.ksteps;
-  cA = (int)(u0 / sc.quota);
-  cB = (int)((u1 - 1) / sc.quota);
+  const int cA = (int)(u0 / sc.quota), cB = (int)((u1 - 1) / sc.quota);
+  return cA == cB ? 0 : cB - cA + 1;
 }
-DAV_HD int fixup_slot(const Sched& sc, int c, int rt) {
-  return ((long long)c * sc.quota >= (long long)rt * sc.ksteps) ? 0 : 1;
+DAV_HD void fixup_piece(const Sched& sc, int rt, int i, int& cta, int& slot) {
+  if (sc.split > 0) {
+    const long long v = (long long)i * sc.rem_tiles + rt;
+    cta = (int)(v % sc.grid);
+    slot = (int)(v / sc.grid);
+    return;
+  }
+  const long long u0 = (long long)rt * sc.ksteps;
+  cta = (int)(u0 / sc.quota) + i;
+  slot = ((long long)cta * sc.quota >= u0) ? 0 : 1;  // the CTA's first segment, or its last one
 }
-// schedule != 0: full waves first (all CTAs on the same k step), the tiles that do not fill a wave as stream-K;
-// schedule == 0: everything stream-K.  max_grid: SM count, already limited by the workspace (2 slots per CTA).
+// schedule 0: everything stream-K.  1: full waves first (all CTAs on the same k step), the tiles that do not fill
+// a wave as stream-K.  2: full waves, then the aligned split-K remainder when it keeps >= 90 % of the CTAs busy
+// (else stream-K).  max_grid: SM count, already limited by the workspace (WS_SLOTS slots per CTA).
 inline Sched make_sched(int tiles, int ksteps, int max_grid, int schedule) {
   Sched sc;
   sc.tiles = tiles;
@@ -184,9 +214,32 @@ inline Sched make_sched(int tiles, int ksteps, int max_grid, int schedule) {
   int grid = (int)std::min<long long>(std::max(max_grid, 1), std::max<long long>(all_units, 1));
   sc.waves = (schedule != 0 && tiles >= grid) ? tiles / grid : 0;
   sc.tile_off = sc.waves * grid;
-  sc.total = (long long)(tiles - sc.tile_off) * ksteps;
+  sc.rem_tiles = tiles - sc.tile_off;
+  sc.total = (long long)sc.rem_tiles * ksteps;
   sc.quota = sc.total > 0 ? (sc.total + grid - 1) / grid : 0;
-  if (sc.waves == 0 && sc.quota > 0) grid = (int)((sc.total + sc.quota - 1) / sc.quota);
+  sc.split = 0;
+  sc.kchunk = 0;
+  if (schedule == 2 && sc.rem_tiles > 0) {
+    const int R = sc.rem_tiles;
+    int best_s = 0;
+    double best_eff = 0.0;
+    const long long smax = std::min<long long>(ksteps, (long long)WS_SLOTS * grid / R);
+    for (int s = 1; s <= smax; ++s) {
+      const int kc = (ksteps + s - 1) / s;
+      if ((ksteps + kc - 1) / kc != s) continue;  // this s leaves an empty last piece
+      const long long pieces = (long long)R * s, rounds = (pieces + grid - 1) / grid;
+      // busy fraction of the rounds (every piece takes kc k steps, the useful work is R * ksteps)
+      const double eff = (double)R * ksteps / ((double)rounds * grid * kc);
+      if (eff > best_eff + 1e-12) { best_eff = eff; best_s = s; }
+    }
+    if (best_s > 0 && best_eff >= 0.9) {
+      sc.split = best_s;
+      sc.kchunk = (ksteps + best_s - 1) / best_s;
+      sc.total = 0;  // no stream-K units
+      sc.quota = 0;
+    }
+  }
+  if (sc.waves == 0 && sc.split == 0 && sc.quota > 0) grid = (int)((sc.total + sc.quota - 1) / sc.quota);
   sc.grid = grid;
   return sc;
 }
@@ -200,7 +253,7 @@ struct Params {
   const double* Xp;    // packed X: [kstep][BK x bpad] in fragment order
   double* W;
   int64_t ldw;
-  double* ws;          // partial tiles: [cta][2][BM x bpad]
+  double* ws;          // partial tiles: [cta][WS_SLOTS][BM x bpad]
 };
 
 // X packed index of element (k, j): ((k/8 * NTT + j/8) * 64 + (j%8)*8 + k%8)
@@ -354,8 +407,8 @@ __global__ void __launch_bounds__(THREADS, 1)
           }
         }
     } else {
-      // partial tile -> workspace slot (0: the CTA's first segment, 1: its last one)
-      double* w = p.ws + ((size_t)blockIdx.x * 2 + sg.slot) * (size_t)(BM * BPAD);
+      // partial tile -> one of the CTA's workspace slots
+      double* w = p.ws + ((size_t)blockIdx.x * WS_SLOTS + sg.slot) * (size_t)(BM * BPAD);
 #pragma unroll
       for (int rg = 0; rg < 2; ++rg)
 #pragma unroll
@@ -374,18 +427,21 @@ __global__ void __launch_bounds__(THREADS, 1)
 
 // Adds the partial tiles of every row tile that was split over several CTAs, in CTA order.
 __global__ void fixup_kernel(int BM, int BPAD, Params p) {
-  const int rt = blockIdx.x;  // tile of the stream-K remainder
+  const int rt = blockIdx.x;  // tile of the remainder
   const int tile = p.sc.tile_off + rt;
-  int cA, cB;
-  fixup_range(p.sc, rt, cA, cB);
-  if (cA == cB) return;  // written directly
+  const int count = fixup_count(p.sc, rt);
+  if (count == 0) return;  // written directly
   const int elems = BM * BPAD;
   for (int e = threadIdx.x; e < elems; e += blockDim.x) {
     const int r = e % BM, j = e / BM;
     const int64_t row = (int64_t)tile * BM + r;
     if (row >= p.M || j >= p.b) continue;
     double s = 0.0;
-    for (int c = cA; c <= cB; ++c) s += p.ws[((size_t)c * 2 + fixup_slot(p.sc, c, rt)) * (size_t)elems + e];
+    for (int i = 0; i < count; ++i) {
+      int cta, slot;
+      fixup_piece(p.sc, rt, i, cta, slot);
+      s += p.ws[((size_t)cta * WS_SLOTS + slot) * (size_t)elems + e];
+    }
     p.W[row + (int64_t)j * p.ldw] = s;
   }
 }
@@ -417,10 +473,10 @@ void launch_cfg(cudaStream_t s, const CUtensorMap& map, Params& p, int ksteps, i
   constexpr int BPAD = NT * WARPS_N * 8;
   constexpr int STAGE_BYTES = BM * BK * 8 + BK * BPAD * 8;
   const size_t slot = (size_t)BM * BPAD;
-  const int max_grid = (int)std::min<size_t>((size_t)num_sms, std::max<size_t>(1, ws_doubles / (2 * slot)));
+  const int max_grid = (int)std::min<size_t>((size_t)num_sms, std::max<size_t>(1, ws_doubles / (WS_SLOTS * slot)));
   p.sc = make_sched((int)ceil_div(p.M, BM), ksteps, max_grid, schedule);
   const int grid = p.sc.grid;
-  const int rem_tiles = p.sc.tiles - p.sc.tile_off;
+  const int rem_tiles = p.sc.rem_tiles;
   p.stages = std::min(MAX_STAGES, (max_smem - 1024 - 256) / STAGE_BYTES);
   if (p.stages < 2) DAV_THROW(DAV_ERR_CUDA, "not enough shared memory for the matvec pipeline");
   p.ws = ws;
@@ -462,7 +518,7 @@ static int schedule_from_env() {
 // Host model of the schedule the kernels execute (same inline functions): enumerates the segments of every CTA and
 // checks that each (row tile, k step) unit is covered exactly once, that a CTA uses each workspace slot at most
 // once, and that the fixup kernel reads exactly the partial segments of each remainder tile.  No device needed.
-// info[8] = {grid, waves, tile_off, quota, tiles, ksteps, partial segments, BM}.  Returns 0 when consistent.
+// info[10] = {grid, waves, tile_off, quota, tiles, ksteps, partial segments, BM, split, kchunk}.  0 = consistent.
 int matvec_schedule_selftest(int64_t M, int64_t K, int b, int num_sms, int schedule, long long* info) {
   if (M <= 0 || K <= 0 || b <= 0 || b > 128 || num_sms <= 0) return -1;
   int warps_n, nt, bpad;
@@ -477,12 +533,12 @@ int matvec_schedule_selftest(int64_t M, int64_t K, int b, int num_sms, int sched
   std::vector<unsigned char> cover((size_t)tiles * ksteps, 0);
   // partial pieces per remainder tile: (cta, slot, ks0, ks1)
   struct Piece { int cta, slot, ks0, ks1; };
-  std::vector<std::vector<Piece>> pieces((size_t)(tiles - sc.tile_off));
+  std::vector<std::vector<Piece>> pieces((size_t)sc.rem_tiles);
   long long npartial = 0;
   for (int c = 0; c < sc.grid; ++c) {
     SegCursor cur = seg_begin(sc, c);
     Segment sg;
-    int slot_used[2] = {0, 0};
+    int slot_used[WS_SLOTS] = {0, 0, 0, 0};
     while (seg_next(sc, c, cur, sg)) {
       if (sg.tile < 0 || sg.tile >= tiles || sg.ks0 < 0 || sg.ks1 > ksteps || sg.ks0 >= sg.ks1) return 2;
       for (int ks = sg.ks0; ks < sg.ks1; ++ks)
@@ -491,7 +547,7 @@ int matvec_schedule_selftest(int64_t M, int64_t K, int b, int num_sms, int sched
       if (complete != (sg.slot < 0)) return 4;
       if (!complete) {
         if (sg.tile < sc.tile_off) return 5;  // a wave tile must be complete
-        if (sg.slot > 1 || slot_used[sg.slot]++) return 6;
+        if (sg.slot >= WS_SLOTS || slot_used[sg.slot]++) return 6;
         pieces[(size_t)(sg.tile - sc.tile_off)].push_back(Piece{c, sg.slot, sg.ks0, sg.ks1});
         ++npartial;
       }
@@ -499,23 +555,29 @@ int matvec_schedule_selftest(int64_t M, int64_t K, int b, int num_sms, int sched
   }
   for (unsigned char v : cover)
     if (v != 1) return 7;  // not covered
-  for (int rt = 0; rt < tiles - sc.tile_off; ++rt) {
-    int cA, cB;
-    fixup_range(sc, rt, cA, cB);
-    const std::vector<Piece>& pc = pieces[(size_t)rt];
-    if (cA == cB) {
+  for (int rt = 0; rt < sc.rem_tiles; ++rt) {
+    std::vector<Piece>& pc = pieces[(size_t)rt];
+    std::sort(pc.begin(), pc.end(), [](const Piece& x, const Piece& y) { return x.ks0 < y.ks0; });
+    const int count = fixup_count(sc, rt);
+    if (count == 0) {
       if (!pc.empty()) return 8;  // fixup would skip a tile that has partial pieces
       continue;
     }
-    if ((int)pc.size() != cB - cA + 1) return 9;
-    for (int c = cA; c <= cB; ++c) {
-      const Piece& q = pc[(size_t)(c - cA)];  // CTAs were enumerated in order
-      if (q.cta != c || q.slot != fixup_slot(sc, c, rt)) return 10;
+    if ((int)pc.size() != count) return 9;
+    int ks = 0;
+    for (int i = 0; i < count; ++i) {  // the fixup pass must read exactly these pieces, in increasing-k order
+      int cta, slot;
+      fixup_piece(sc, rt, i, cta, slot);
+      const Piece& q = pc[(size_t)i];
+      if (q.cta != cta || q.slot != slot) return 10;
+      if (q.ks0 != ks) return 11;
+      ks = q.ks1;
     }
+    if (ks != ksteps) return 12;
   }
   if (info) {
     info[0] = sc.grid; info[1] = sc.waves; info[2] = sc.tile_off; info[3] = sc.quota;
-    info[4] = tiles; info[5] = ksteps; info[6] = npartial; info[7] = BM;
+    info[4] = tiles; info[5] = ksteps; info[6] = npartial; info[7] = BM; info[8] = sc.split; info[9] = sc.kchunk;
   }
   return 0;
 }
@@ -556,7 +618,7 @@ MatvecPlan* matvec_plan_create(const double* A, int64_t M, int64_t K, int64_t ld
   }
   const int bmax = (int)std::min<int64_t>(round_up(std::max(max_b, 8), 8), 128);
   p->Xp.alloc((size_t)round_up(K, BK) * bmax);
-  p->ws.alloc((size_t)p->num_sms * 2 * 256 * 32);  // BM x BPAD <= 8192 for every config
+  p->ws.alloc((size_t)p->num_sms * WS_SLOTS * 256 * 32);  // BM x BPAD <= 8192 for every config
   return p;
 }
 

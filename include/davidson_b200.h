@@ -185,9 +185,10 @@ int dav_bench_block_matvec(dav_solver_t* h, int which, int64_t b, int reps, floa
 /* Host-only check of the block-matvec work schedule (full waves + stream-K remainder) for an M x K local block and
  * a b-column block on a device with num_sms SMs: runs the very functions the kernel and its fixup pass use and
  * verifies that every (row tile, k step) unit is computed exactly once and every partial tile is summed exactly
- * once.  schedule: 0 = pure stream-K, 1 = waves + stream-K, < 0 = what DAV_MATVEC_SCHEDULE / the default selects.
- * info[8] (may be NULL) = {grid, waves, first remainder tile, remainder quota, tiles, k steps, partial segments,
- * tile rows}.  Needs no GPU.  Returns DAV_OK or DAV_ERR_INVALID (dav_last_error() names the failed check). */
+ * once.  schedule: 0 = pure stream-K, 1 = waves + stream-K remainder, 2 = waves + aligned split-K remainder,
+ * < 0 = what DAV_MATVEC_SCHEDULE / the default selects.
+ * info[10] (may be NULL) = {grid, waves, first remainder tile, stream-K quota, tiles, k steps, partial segments,
+ * tile rows, split-K pieces per remainder tile (0 = stream-K), k steps per piece}.  Needs no GPU.  Returns DAV_OK or DAV_ERR_INVALID (dav_last_error() names the failed check). */
 int dav_debug_matvec_schedule(int64_t m, int64_t k, int b, int num_sms, int schedule, long long* info);
 
 /* =============================================================================================

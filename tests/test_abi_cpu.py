@@ -42,13 +42,13 @@ def test_partition_rows_tiles_the_matrix():
     assert L.dav_partition_rows(C.c_int64(10), 2, 5, C.byref(b), C.byref(e)) != 0
 
 
-@pytest.mark.parametrize("schedule", [0, 1])
+@pytest.mark.parametrize("schedule", [0, 1, 2])
 def test_matvec_schedule_covers_every_unit_once(schedule):
     """The (full waves + stream-K remainder) work split of the block matvec, checked with the functions the kernel
     itself runs: every (row tile, k step) unit exactly once, every partial tile summed exactly once."""
     L = fd.lib()
     L.dav_debug_matvec_schedule.argtypes = [C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
-    info = (C.c_longlong * 8)()
+    info = (C.c_longlong * 10)()
     shapes = [(1, 1), (50, 50), (255, 300), (256, 16), (257, 17), (1000, 1000), (4097, 4097), (12500, 20000),
               (37888, 2000), (37889, 999), (75776, 640), (100000, 1600), (20000, 20000), (1, 5000), (70000, 33)]
     for m, k in shapes:
@@ -56,7 +56,7 @@ def test_matvec_schedule_covers_every_unit_once(schedule):
             for sms in (148, 132, 7, 1):
                 rc = L.dav_debug_matvec_schedule(m, k, b, sms, schedule, info)
                 assert rc == 0, (m, k, b, sms, fd.lib().dav_last_error())
-                grid, waves, tile_off, quota, tiles, ksteps, npartial, bm = list(info)
+                grid, waves, tile_off, quota, tiles, ksteps, npartial, bm, split, kchunk = list(info)
                 assert 1 <= grid <= sms and tiles == -(-m // bm) and ksteps == -(-k // 16)
                 if schedule == 0:
                     assert waves == 0 and tile_off == 0
@@ -67,6 +67,9 @@ def test_matvec_schedule_covers_every_unit_once(schedule):
     # the headline shape: n = 100,000 on 148 SMs, b = 32 -> 391 tiles = 2 full waves + 95 stream-K tiles
     assert L.dav_debug_matvec_schedule(100000, 100000, 32, 148, 1, info) == 0
     assert list(info)[:3] == [148, 2, 296] and info[4] == 391
+    # ... and with the aligned split-K remainder: 95 tiles x 3 pieces = 285 pieces in 2 rounds of 148 CTAs
+    assert L.dav_debug_matvec_schedule(100000, 100000, 32, 148, 2, info) == 0
+    assert list(info)[:3] == [148, 2, 296] and info[8] == 3 and info[9] == 2084 and info[6] == 285
 
 
 def test_no_cpu_fallback():

@@ -92,6 +92,40 @@ def test_block_matvec_parity(impl, n, b):
     s.close()
 
 
+@pytest.mark.parametrize("n,b,uploaded", [(1000, 5, True), (4097, 33, True), (3000, 64, True), (9700, 128, True),
+                                          (9473, 100, True), (19100, 64, False), (19000, 40, False),
+                                          (38100, 16, False), (37888, 32, False), (76000, 8, False)])
+def test_block_matvec_schedules(n, b, uploaded, monkeypatch):
+    """The work schedules of the block matvec -- full waves + stream-K remainder (DAV_MATVEC_SCHEDULE=1), full waves +
+    aligned split-K remainder (=2) -- against pure stream-K (=0) and the SIMT kernel, at sizes with and without a
+    full wave of row tiles on 148 SMs (tile rows: 64 for b > 64, 128 for b > 32, else 256)."""
+    rng = np.random.default_rng(n + b)
+    X = rng.standard_normal((n, b))
+    s = fd.DavidsonSolver()
+    if uploaded:
+        A = orc.generate_diagonal_dominant(n, 1e-3, seed=n) + 0.01 * rng.standard_normal((n, n))
+        s.upload(0, A)
+    else:
+        s.generate_diagonal_dominant(0, n, 1e-4, None, 3)
+    s.set_matvec_impl(dv.MATVEC_TMA_DMMA)
+    W = {}
+    for sched in (0, 1, 2):
+        monkeypatch.setenv("DAV_MATVEC_SCHEDULE", str(sched))
+        W[sched] = s.block_matvec(0, X)
+        assert np.array_equal(W[sched], s.block_matvec(0, X))  # bit reproducible
+    s.set_matvec_impl(dv.MATVEC_SIMT)
+    Ws = s.block_matvec(0, X)
+    s.close()
+    scale = np.abs(Ws).max()
+    for sched in (1, 2):
+        assert np.abs(W[sched] - W[0]).max() <= 1e-13 * scale, sched
+        assert np.abs(W[sched] - Ws).max() <= 1e-12 * scale, sched
+    if uploaded:
+        ref = A @ X
+        for sched in (0, 1, 2):
+            assert np.abs(W[sched] - ref).max() <= 1e-12 * np.abs(ref).max(), sched
+
+
 def test_block_matvec_linearity_large():
     """Size-independent property at a size the oracle would not finish quickly: A(x+2y) == Ax + 2Ay and
     device-generated A equals the oracle's stream on a sampled sub-block."""
