@@ -33,7 +33,7 @@ namespace dav {
 
 namespace {
 
-constexpr int BK = 16;            // k columns per pipeline stage
+constexpr int BK_DEFAULT = 16;    // k columns per pipeline stage (DAV_MATVEC_BK=32 selects the deeper stage)
 constexpr int CONSUMERS = 8;      // consumer warps
 constexpr int THREADS = (CONSUMERS + 1) * 32;
 constexpr int MAX_STAGES = 8;
@@ -274,7 +274,7 @@ __global__ void pack_x_kernel(int64_t K, int64_t Kpad, int b, int bpad, const do
   }
 }
 
-template <int NT, int WARPS_N>
+template <int NT, int WARPS_N, int BK>
 __global__ void __launch_bounds__(THREADS, 1)
     matvec_kernel(const __grid_constant__ CUtensorMap tmapA, const Params p) {
   constexpr int WARPS_M = CONSUMERS / WARPS_N;
@@ -309,11 +309,10 @@ __global__ void __launch_bounds__(THREADS, 1)
   if (warp == CONSUMERS) {
     // ================= TMA producer (one elected lane) =================
     if (lane == 0) {
-      long long it = 0;
+      int s = 0;        // ring position and phase bit, kept incrementally (no 64-bit division per stage)
+      uint32_t ph = 0;
       const uint64_t pol_a = policy_evict_first(), pol_x = policy_evict_last();
       auto load_stage = [&](int tile, int ks) {
-        const int s = (int)(it % S);
-        const uint32_t ph = (uint32_t)((it / S) & 1);
         mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
         const uint32_t fb = smem_u32(&full_bar[s]);
         mbar_expect_tx(fb, STAGE_BYTES);
@@ -331,7 +330,7 @@ __global__ void __launch_bounds__(THREADS, 1)
           bulk_load_1d(a_dst + A_BYTES, p.Xp + (size_t)ks * (BK * BPAD), X_BYTES, fb, pol_x);
         else
           bulk_load_1d_nohint(a_dst + A_BYTES, p.Xp + (size_t)ks * (BK * BPAD), X_BYTES, fb);
-        ++it;
+        if (++s == S) { s = 0; ph ^= 1u; }
       };
       while (seg_next(sc, (int)blockIdx.x, cur, sg))
         for (int ks = sg.ks0; ks < sg.ks1; ++ks) load_stage(sg.tile, ks);
@@ -350,7 +349,8 @@ __global__ void __launch_bounds__(THREADS, 1)
   const uint32_t a_lane = (uint32_t)(wr * 2) * (BK * 128);
   const uint32_t x_lane = A_BYTES + (uint32_t)((wc * NT) * 64 + g * 8 + 2 * t) * 8;
 
-  long long it = 0;
+  int s = 0;        // ring position and phase bit of the next stage to consume
+  uint32_t ph = 0;
   while (seg_next(sc, (int)blockIdx.x, cur, sg)) {
     const int tile = sg.tile, ks0 = sg.ks0, ks1 = sg.ks1;
 #pragma unroll
@@ -360,9 +360,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
         for (int n = 0; n < NT; ++n) acc[a][e][n][0] = acc[a][e][n][1] = 0.0;
 
-    for (int ks = ks0; ks < ks1; ++ks, ++it) {
-      const int s = (int)(it % S);
-      const uint32_t ph = (uint32_t)((it / S) & 1);
+    for (int ks = ks0; ks < ks1; ++ks) {
       mbar_wait(smem_u32(&full_bar[s]), ph);
       const uint32_t sb = base + (uint32_t)s * STAGE_BYTES;
 #pragma unroll
@@ -388,6 +386,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&empty_bar[s]));
+      if (++s == S) { s = 0; ph ^= 1u; }
     }
 
     if (sg.slot < 0) {
@@ -466,7 +465,7 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <int NT, int WARPS_N>
+template <int NT, int WARPS_N, int BK>
 void launch_cfg(cudaStream_t s, const CUtensorMap& map, Params& p, int ksteps, int max_smem, int num_sms, double* ws,
                 size_t ws_doubles, int schedule) {
   constexpr int BM = (CONSUMERS / WARPS_N) * 32;
@@ -483,10 +482,10 @@ void launch_cfg(cudaStream_t s, const CUtensorMap& map, Params& p, int ksteps, i
   const size_t smem = (size_t)p.stages * STAGE_BYTES + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    CK(cudaFuncSetAttribute(matvec_kernel<NT, WARPS_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 256));
+    CK(cudaFuncSetAttribute(matvec_kernel<NT, WARPS_N, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 256));
     attr_set = true;
   }
-  matvec_kernel<NT, WARPS_N><<<grid, THREADS, smem, s>>>(map, p);
+  matvec_kernel<NT, WARPS_N, BK><<<grid, THREADS, smem, s>>>(map, p);
   CK_LAUNCH();
   ++g_kernel_launches;
   if (rem_tiles > 0) {
@@ -509,6 +508,11 @@ static void pick_cfg(int bc, int* warps_n, int* nt, int* bpad) {
   *bpad = *nt * *warps_n * 8;
 }
 
+static int bk_from_env() {
+  const char* e = std::getenv("DAV_MATVEC_BK");
+  return (e && std::atoi(e) == 32) ? 32 : BK_DEFAULT;
+}
+
 static int schedule_from_env() {
   // 1: full waves + stream-K remainder; 0: pure stream-K.  Read per call so one process can compare the two.
   const char* e = std::getenv("DAV_MATVEC_SCHEDULE");
@@ -525,6 +529,7 @@ int matvec_schedule_selftest(int64_t M, int64_t K, int b, int num_sms, int sched
   pick_cfg(b, &warps_n, &nt, &bpad);
   const int BM = (CONSUMERS / warps_n) * 32;
   const int tiles = (int)ceil_div(M, (int64_t)BM);
+  const int BK = bk_from_env();
   const int ksteps = (int)(round_up(K, BK) / BK);
   if (schedule < 0) schedule = schedule_from_env();
   const Sched sc = make_sched(tiles, ksteps, num_sms, schedule);
@@ -583,7 +588,7 @@ int matvec_schedule_selftest(int64_t M, int64_t K, int b, int num_sms, int sched
 }
 
 struct MatvecPlan {
-  CUtensorMap map;
+  CUtensorMap map, map32;  // boxes of 16 rows x 16 / 32 columns
   const double* A;
   int64_t M, K, lda;
   int max_b;
@@ -607,17 +612,19 @@ MatvecPlan* matvec_plan_create(const double* A, int64_t M, int64_t K, int64_t ld
   if (p->num_sms <= 0) p->num_sms = NUM_SMS_FALLBACK;
   cuuint64_t gdim[2] = {(cuuint64_t)M, (cuuint64_t)K};
   cuuint64_t gstride[1] = {(cuuint64_t)lda * 8};
-  cuuint32_t box[2] = {16, (cuuint32_t)BK};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(&p->map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)A, gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    delete p;
-    DAV_THROW(DAV_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  for (int v = 0; v < 2; ++v) {
+    cuuint32_t box[2] = {16, (cuuint32_t)(v ? 32 : 16)};
+    CUresult r = enc(v ? &p->map32 : &p->map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)A, gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      delete p;
+      DAV_THROW(DAV_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    }
   }
   const int bmax = (int)std::min<int64_t>(round_up(std::max(max_b, 8), 8), 128);
-  p->Xp.alloc((size_t)round_up(K, BK) * bmax);
+  p->Xp.alloc((size_t)round_up(K, 32) * bmax);
   p->ws.alloc((size_t)p->num_sms * WS_SLOTS * 256 * 32);  // BM x BPAD <= 8192 for every config
   return p;
 }
@@ -626,6 +633,7 @@ void matvec_plan_destroy(MatvecPlan* p) { delete p; }
 
 void matvec_dmma(cudaStream_t s, MatvecPlan* plan, int b, const double* X, int64_t ldx, double* W, int64_t ldw) {
   if (b <= 0 || plan->M <= 0) return;
+  const int BK = bk_from_env();
   const int64_t Kpad = round_up(plan->K, BK);
   for (int j0 = 0; j0 < b; j0 += 128) {
     const int bc = std::min(128, b - j0);
@@ -650,8 +658,15 @@ void matvec_dmma(cudaStream_t s, MatvecPlan* plan, int b, const double* X, int64
       p.l2_hints = hints;
     }
     const int schedule = schedule_from_env();
-#define CFG(NT_, WN_)                                                                                      \
-  launch_cfg<NT_, WN_>(s, plan->map, p, ksteps, plan->max_smem, plan->num_sms, plan->ws.p, plan->ws.n, schedule)
+#define CFG(NT_, WN_)                                                                                          \
+  do {                                                                                                         \
+    if (BK == 32)                                                                                              \
+      launch_cfg<NT_, WN_, 32>(s, plan->map32, p, ksteps, plan->max_smem, plan->num_sms, plan->ws.p, plan->ws.n, \
+                               schedule);                                                                      \
+    else                                                                                                       \
+      launch_cfg<NT_, WN_, 16>(s, plan->map, p, ksteps, plan->max_smem, plan->num_sms, plan->ws.p, plan->ws.n,   \
+                               schedule);                                                                      \
+  } while (0)
     if (warps_n == 1) {
       switch (nt) {
         case 1: CFG(1, 1); break;

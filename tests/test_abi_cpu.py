@@ -42,10 +42,12 @@ def test_partition_rows_tiles_the_matrix():
     assert L.dav_partition_rows(C.c_int64(10), 2, 5, C.byref(b), C.byref(e)) != 0
 
 
+@pytest.mark.parametrize("bk", [16, 32])
 @pytest.mark.parametrize("schedule", [0, 1, 2])
-def test_matvec_schedule_covers_every_unit_once(schedule):
+def test_matvec_schedule_covers_every_unit_once(schedule, bk, monkeypatch):
     """The (full waves + stream-K remainder) work split of the block matvec, checked with the functions the kernel
     itself runs: every (row tile, k step) unit exactly once, every partial tile summed exactly once."""
+    monkeypatch.setenv("DAV_MATVEC_BK", str(bk))  # columns of A per pipeline stage -> number of k steps
     L = fd.lib()
     L.dav_debug_matvec_schedule.argtypes = [C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
     info = (C.c_longlong * 10)()
@@ -57,7 +59,7 @@ def test_matvec_schedule_covers_every_unit_once(schedule):
                 rc = L.dav_debug_matvec_schedule(m, k, b, sms, schedule, info)
                 assert rc == 0, (m, k, b, sms, fd.lib().dav_last_error())
                 grid, waves, tile_off, quota, tiles, ksteps, npartial, bm, split, kchunk = list(info)
-                assert 1 <= grid <= sms and tiles == -(-m // bm) and ksteps == -(-k // 16)
+                assert 1 <= grid <= sms and tiles == -(-m // bm) and ksteps == -(-k // bk)
                 if schedule == 0:
                     assert waves == 0 and tile_off == 0
                 else:
@@ -67,6 +69,8 @@ def test_matvec_schedule_covers_every_unit_once(schedule):
     # the headline shape: n = 100,000 on 148 SMs, b = 32 -> 391 tiles = 2 full waves + 95 stream-K tiles
     assert L.dav_debug_matvec_schedule(100000, 100000, 32, 148, 1, info) == 0
     assert list(info)[:3] == [148, 2, 296] and info[4] == 391
+    if bk != 16:
+        return
     # ... and with the aligned split-K remainder: 95 tiles x 3 pieces = 285 pieces in 2 rounds of 148 CTAs
     assert L.dav_debug_matvec_schedule(100000, 100000, 32, 148, 2, info) == 0
     assert list(info)[:3] == [148, 2, 296] and info[8] == 3 and info[9] == 2084 and info[6] == 285

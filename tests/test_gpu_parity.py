@@ -97,8 +97,9 @@ def test_block_matvec_parity(impl, n, b):
                                           (38100, 16, False), (37888, 32, False), (76000, 8, False)])
 def test_block_matvec_schedules(n, b, uploaded, monkeypatch):
     """The work schedules of the block matvec -- full waves + stream-K remainder (DAV_MATVEC_SCHEDULE=1), full waves +
-    aligned split-K remainder (=2) -- against pure stream-K (=0) and the SIMT kernel, at sizes with and without a
-    full wave of row tiles on 148 SMs (tile rows: 64 for b > 64, 128 for b > 32, else 256)."""
+    aligned split-K remainder (=2) -- and both pipeline-stage depths (DAV_MATVEC_BK=16/32 columns of A per stage)
+    against pure stream-K (=0) and the SIMT kernel, at sizes with and without a full wave of row tiles on 148 SMs
+    (tile rows: 64 for b > 64, 128 for b > 32, else 256)."""
     rng = np.random.default_rng(n + b)
     X = rng.standard_normal((n, b))
     s = fd.DavidsonSolver()
@@ -109,21 +110,23 @@ def test_block_matvec_schedules(n, b, uploaded, monkeypatch):
         s.generate_diagonal_dominant(0, n, 1e-4, None, 3)
     s.set_matvec_impl(dv.MATVEC_TMA_DMMA)
     W = {}
-    for sched in (0, 1, 2):
+    variants = [(sched, bk) for bk in (16, 32) for sched in (0, 1, 2)]
+    for sched, bk in variants:
         monkeypatch.setenv("DAV_MATVEC_SCHEDULE", str(sched))
-        W[sched] = s.block_matvec(0, X)
-        assert np.array_equal(W[sched], s.block_matvec(0, X))  # bit reproducible
+        monkeypatch.setenv("DAV_MATVEC_BK", str(bk))
+        W[sched, bk] = s.block_matvec(0, X)
+        assert np.array_equal(W[sched, bk], s.block_matvec(0, X))  # bit reproducible
     s.set_matvec_impl(dv.MATVEC_SIMT)
     Ws = s.block_matvec(0, X)
     s.close()
     scale = np.abs(Ws).max()
-    for sched in (1, 2):
-        assert np.abs(W[sched] - W[0]).max() <= 1e-13 * scale, sched
-        assert np.abs(W[sched] - Ws).max() <= 1e-12 * scale, sched
+    for v in variants:
+        assert np.abs(W[v] - W[0, 16]).max() <= 1e-13 * scale, v
+        assert np.abs(W[v] - Ws).max() <= 1e-12 * scale, v
     if uploaded:
         ref = A @ X
-        for sched in (0, 1, 2):
-            assert np.abs(W[sched] - ref).max() <= 1e-12 * np.abs(ref).max(), sched
+        for v in variants:
+            assert np.abs(W[v] - ref).max() <= 1e-12 * np.abs(ref).max(), v
 
 
 def test_block_matvec_linearity_large():
