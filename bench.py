@@ -319,18 +319,28 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); torch.matmul(a, bb); e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
-    p64 = 2.0 * 8192 ** 3 / best * 1e-9
+    p64_cublas = 2.0 * 8192 ** 3 / best * 1e-9
     del a, bb
     torch.cuda.empty_cache()
+    # ... and the DMMA issue rate of the chip from registers (csrc/microbench.cu): what the FP64 tensor pipe can do
+    # with no memory system at all.  The roofline denominator is the larger of the two.
+    try:
+        p64_pipe = float(solver.bench_fp64_pipe(3))
+    except Exception:
+        p64_pipe = 0.0
+    p64 = max(p64_cublas, p64_pipe)
     dom_b = int(st.last_matvec_b)
     dom = per_width.get(str(dom_b), per_width[str(widths[-1])])
     in_solve_ms = max_over_ranks(sum(mv_ms) / len(mv_ms))
     roofline = {"bound": "tensor", "achieved": dom["TFLOPs"], "peak": p64, "unit": "TFLOP/s",
                 "frac": dom["TFLOPs"] / p64, "traffic": None,
-                "kernel": "matvec_kernel (TMA + mbarrier + FP64 DMMA, stream-K), widest block of the solve b=%d: "
+                "kernel": "matvec_kernel (TMA + mbarrier + FP64 DMMA, stream-K, 32-column stages), widest block of the solve b=%d: "
                           "2*nl*n*b flops / launch; FP64-bound above b~23 (b/4 flop per byte vs %.1f flop/B machine "
                           "balance)" % (dom_b, p64 * 1e3 / hbm_peak),
-                "peak_source": "measured live: torch.matmul fp64 8192^3 (cuBLAS DGEMM), best of 3",
+                "peak_source": "measured live, larger of: register-only DMMA microbenchmark %.2f TFLOP/s "
+                               "(dav_bench_fp64_pipe), cuBLAS DGEMM 8192^3 through torch.matmul %.2f TFLOP/s"
+                               % (p64_pipe, p64_cublas),
+                "peak_cublas_dgemm": p64_cublas, "peak_dmma_pipe": p64_pipe,
                 "hbm_view": {"b": 16, "achieved": per_width["16"]["GBps"], "peak": hbm_peak, "unit": "GB/s",
                              "frac": per_width["16"]["hbm_frac"], "peak_source": hbm_src,
                              "note": "narrow block (HBM-bound regime): algorithmic bytes 8*nl*n + 8*n*b + 8*nl*b"},

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdavidson_b200.so")
+# DAV_B200_LIB: load another build of the same C ABI (diagnostics: A/B of two builds in scripts/)
+LIB_PATH = os.environ.get("DAV_B200_LIB") or os.path.join(HERE, "libdavidson_b200.so")
 
 GEMV_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int64, C.c_int64, C.c_void_p)
 
@@ -23,7 +24,7 @@ SYMBOLS = [
     "dav_generate_preconditioner", "dav_norm", "dav_lapack_generalized_eigensolver",
     "dav_lapack_generalized_eigensolver_lowest", "dav_sym_eigh_info", "dav_lapack_qr", "dav_lapack_solver", "dav_lapack_matmul",
     "dav_lapack_matrix_vector", "dav_lapack_sort", "dav_free_matmul", "dav_compute_on_the_fly",
-    "dav_debug_matvec_schedule",
+    "dav_debug_matvec_schedule", "dav_bench_fp64_pipe",
 ]
 
 

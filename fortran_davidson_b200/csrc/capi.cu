@@ -148,6 +148,14 @@ int dav_partition_rows(int64_t n, int world_size, int rank, int64_t* row_begin, 
   return DAV_OK;
 }
 
+int dav_bench_fp64_pipe(dav_solver_t* h, int reps, double* dmma_tflops) {
+  API_BEGIN
+  need(h && dmma_tflops && reps >= 1, "bad arguments");
+  CK(cudaSetDevice(h->device));
+  *dmma_tflops = dmma_peak_tflops(h->stream, reps);
+  API_END
+}
+
 int dav_debug_matvec_schedule(int64_t m, int64_t k, int b, int num_sms, int schedule, long long* info) {
   API_BEGIN
   const int rc = matvec_schedule_selftest(m, k, b, num_sms, schedule, info);

@@ -27,6 +27,9 @@ void matvec_dmma(cudaStream_t s, MatvecPlan* plan, int b, const double* X, int64
 // host model of the (waves + stream-K) schedule the kernel executes; see matvec_dmma.cu.  0 = consistent.
 int matvec_schedule_selftest(int64_t M, int64_t K, int b, int num_sms, int schedule, long long* info);
 
+// ---- microbench.cu : measured FP64 tensor-pipe peak (denominator of the roofline in bench.py) ----------------
+double dmma_peak_tflops(cudaStream_t s, int reps);
+
 // ---- freeops.cu : on-the-fly operators (benchmark_free.f90:38-76, tests/test_utils.f90:37-116) --
 // W(rows row0..row0+nl) = Op * X(n x b); etab[n] = (double)expf(i/n) table (built on host with glibc expf).
 void free_matmul_builtin(cudaStream_t s, int op, int64_t n, int64_t row0, int64_t nl, int b, const double* etab,

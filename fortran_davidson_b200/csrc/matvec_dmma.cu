@@ -33,7 +33,7 @@ namespace dav {
 
 namespace {
 
-constexpr int BK_DEFAULT = 16;    // k columns per pipeline stage (DAV_MATVEC_BK=32 selects the deeper stage)
+constexpr int BK_DEFAULT = 32;    // k columns of A per pipeline stage (DAV_MATVEC_BK=16 selects the shallower stage)
 constexpr int CONSUMERS = 8;      // consumer warps
 constexpr int THREADS = (CONSUMERS + 1) * 32;
 constexpr int MAX_STAGES = 8;
@@ -314,6 +314,11 @@ __global__ void __launch_bounds__(THREADS, 1)
       const uint64_t pol_a = policy_evict_first(), pol_x = policy_evict_last();
       auto load_stage = [&](int tile, int ks) {
         mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+        // The consumers read this slot with ld.shared (generic proxy); the refill below writes it through the async
+        // proxy.  Write-after-read across the two proxies needs a proxy fence between the acquire above and the TMA
+        // issue -- without it the refill overtook late fragment loads once the producer stopped spending ~500
+        // cycles per stage on 64-bit divisions (scripts/matvec_stress.py: 27 of 30 runs wrong at n=2048, b=128).
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         const uint32_t fb = smem_u32(&full_bar[s]);
         mbar_expect_tx(fb, STAGE_BYTES);
         const uint32_t a_dst = base + (uint32_t)s * STAGE_BYTES;
@@ -384,7 +389,12 @@ __global__ void __launch_bounds__(THREADS, 1)
           }
         }
       }
+      // Release the slot only when every fragment load of this stage has returned: ptxas schedules the arrive
+      // right behind the last LDS *issue* (it has no register dependency on the loaded data, the 30-odd DMMAs that
+      // consume it come later), so the block fence -- which waits for the warp's outstanding shared-memory loads --
+      // goes between them.  Measured cost: none (the other warp of the sub-partition owns the DMMA pipe meanwhile).
       __syncwarp();
+      __threadfence_block();
       if (lane == 0) mbar_arrive(smem_u32(&empty_bar[s]));
       if (++s == S) { s = 0; ph ^= 1u; }
     }
@@ -510,7 +520,8 @@ static void pick_cfg(int bc, int* warps_n, int* nt, int* bpad) {
 
 static int bk_from_env() {
   const char* e = std::getenv("DAV_MATVEC_BK");
-  return (e && std::atoi(e) == 32) ? 32 : BK_DEFAULT;
+  const int v = e ? std::atoi(e) : BK_DEFAULT;
+  return (v == 16 || v == 32) ? v : BK_DEFAULT;
 }
 
 static int schedule_from_env() {

@@ -233,6 +233,12 @@ class DavidsonSolver:
                                      dp(w), C.c_int64(max(r1 - r0, 1))))
         return w
 
+    def bench_fp64_pipe(self, reps=3):
+        """Measured DMMA (FP64 tensor pipe) peak of this device in TFLOP/s (register-only kernel)."""
+        out = C.c_double(0.0)
+        check(lib().dav_bench_fp64_pipe(self._h, C.c_int(reps), C.byref(out)))
+        return out.value
+
     def bench_block_matvec(self, which, b, reps):
         ms = (C.c_float * reps)()
         check(lib().dav_bench_block_matvec(self._h, C.c_int(which), C.c_int64(b), C.c_int(reps), ms))

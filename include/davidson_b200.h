@@ -182,6 +182,10 @@ int dav_block_matvec(dav_solver_t* h, int which, int64_t b, const double* x, int
  * stream (X = deterministic pseudo-random block kept on device).  ms_out[reps]. */
 int dav_bench_block_matvec(dav_solver_t* h, int which, int64_t b, int reps, float* ms_out);
 
+/* Measured FP64 tensor-pipe peak of the handle's device: TFLOP/s of back-to-back DMMA.8x8x4 (mma.sync.m8n8k4.f64) from
+ * registers on every SM, best of `reps` launches of ~2 ms.  Denominator of the FP64 roofline in bench.py. */
+int dav_bench_fp64_pipe(dav_solver_t* h, int reps, double* dmma_tflops);
+
 /* Host-only check of the block-matvec work schedule (full waves + stream-K remainder) for an M x K local block and
  * a b-column block on a device with num_sms SMs: runs the very functions the kernel and its fixup pass use and
  * verifies that every (row tile, k step) unit is computed exactly once and every partial tile is summed exactly
