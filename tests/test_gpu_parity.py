@@ -146,6 +146,27 @@ def test_block_matvec_linearity_large():
     s.close()
 
 
+@pytest.mark.parametrize("ta,m,k,n", [("N", 1000, 37, 5), ("N", 4099, 128, 64), ("N", 100, 100, 100), ("N", 70001, 64, 33),
+                                      ("N", 20000, 256, 128), ("N", 1, 1, 1), ("N", 65, 3, 129),
+                                      ("T", 70, 5000, 33), ("T", 128, 100000, 64), ("T", 1, 3, 1), ("T", 256, 20011, 128),
+                                      ("T", 64, 12500, 32), ("T", 33, 1000, 130)])
+def test_gemm_tensor_pipe_variant(ta, m, k, n, monkeypatch):
+    """The tall-skinny products around the matvec (lapack_matmul call sites of davidson.f90:131,159,218,223) on the
+    SIMT kernel (DAV_GEMM_IMPL=0) and on the DMMA kernel (=1) against numpy; m x n = op(A) (m x k) * B (k x n)."""
+    from fortran_davidson_b200 import lapack_wrapper as lw
+    rng = np.random.default_rng(m * 7 + k * 3 + n)
+    A = rng.standard_normal((k, m) if ta == "T" else (m, k))
+    B = rng.standard_normal((k, n))
+    ref = (A.T if ta == "T" else A) @ B
+    tol = 1e-13 * max(1.0, np.abs(ref).max()) * max(1.0, np.sqrt(k) / 4)
+    out = {}
+    for impl in ("0", "1"):
+        monkeypatch.setenv("DAV_GEMM_IMPL", impl)
+        out[impl] = lw.lapack_matmul(ta, "N", A, B, 0.5)
+        assert np.abs(out[impl] - 0.5 * ref).max() <= tol, impl
+        assert np.array_equal(out[impl], lw.lapack_matmul(ta, "N", A, B, 0.5))  # deterministic split-K reduction
+
+
 # ---------------------------------------------------------------- lapack_wrapper / array_utils mirrors
 def test_lapack_wrapper_mirrors():
     lw, au = fd.lapack_wrapper, fd.array_utils
