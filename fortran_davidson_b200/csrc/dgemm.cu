@@ -23,6 +23,7 @@ thread_local long long g_kernel_launches = 0;
 namespace {
 
 constexpr int BM = 64, BN = 64, BK = 16, LDS_ = 66, NT = 256;
+constexpr int GEMM_SPLIT_TARGET_DEFAULT = 296;  // CTAs a split-K launch aims for (DAV_GEMM_SPLIT_TARGET overrides)
 constexpr int GEMM_IMPL_DEFAULT = 1;  // 1: tensor-pipe kernel, 0: SIMT kernel (DAV_GEMM_IMPL overrides)
 
 template <bool TA>
@@ -230,9 +231,14 @@ void gemm(cudaStream_t s, bool transA, int64_t M, int64_t N, int64_t K, double a
   if (M <= 0 || N <= 0) return;
   const int64_t gx = ceil_div(M, BM), gy = ceil_div(N, BN);
   int splits = 1;
+  // read per call so one process can compare the two implementations (tests, bench A/B)
+  const char* impl_env = std::getenv("DAV_GEMM_IMPL");
+  const int impl = impl_env ? std::atoi(impl_env) : GEMM_IMPL_DEFAULT;
   if (K > 1024 && gx * gy < 592) {  // long reduction, few output tiles: split K over the grid
     // about two CTAs per SM in total: more partials only lengthen the reduction (each is M x N doubles of traffic)
-    splits = (int)std::min<int64_t>(ceil_div(296, gx * gy), ceil_div(K, 256));
+    const char* tgt_env = std::getenv("DAV_GEMM_SPLIT_TARGET");
+    const int64_t target = tgt_env ? std::max(1, std::atoi(tgt_env)) : GEMM_SPLIT_TARGET_DEFAULT;
+    splits = (int)std::min<int64_t>(ceil_div(target, gx * gy), ceil_div(K, 256));
     const size_t need = (size_t)M * (size_t)N;
     if (ws == nullptr || need == 0) splits = 1;
     else splits = (int)std::min<size_t>((size_t)splits, ws_doubles / need);
@@ -242,9 +248,6 @@ void gemm(cudaStream_t s, bool transA, int64_t M, int64_t N, int64_t K, double a
   splits = (int)ceil_div(std::max<int64_t>(K, 1), Kchunk);
   if (gy > 65535 || splits > 65535) DAV_THROW(DAV_ERR_INVALID, "gemm grid too large");
   dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)splits);
-  // read per call so one process can compare the two implementations (tests, bench A/B)
-  const char* impl_env = std::getenv("DAV_GEMM_IMPL");
-  const int impl = impl_env ? std::atoi(impl_env) : GEMM_IMPL_DEFAULT;
   if (impl == 1 && transA)
     gemm_dmma_kernel<true><<<grid, 128, 0, s>>>(M, N, K, Kchunk, alpha, A, lda, B, ldb, beta, C, ldc, ws, splits);
   else if (impl == 1)
