@@ -334,7 +334,7 @@ def main():
     in_solve_ms = max_over_ranks(sum(mv_ms) / len(mv_ms))
     roofline = {"bound": "tensor", "achieved": dom["TFLOPs"], "peak": p64, "unit": "TFLOP/s",
                 "frac": dom["TFLOPs"] / p64, "traffic": None,
-                "kernel": "matvec_kernel (TMA + mbarrier + FP64 DMMA, stream-K, 32-column stages), widest block of the solve b=%d: "
+                "kernel": "matvec_kernel (TMA + mbarrier + FP64 DMMA, 32-column stages; full waves + stream-K remainder for b > 32, stream-K below), widest block of the solve b=%d: "
                           "2*nl*n*b flops / launch; FP64-bound above b~23 (b/4 flop per byte vs %.1f flop/B machine "
                           "balance)" % (dom_b, p64 * 1e3 / hbm_peak),
                 "peak_source": "measured live, larger of: register-only DMMA microbenchmark %.2f TFLOP/s "

@@ -10,7 +10,7 @@
 //     pages for every SM, one X tile shared through L2).  The tiles that do not fill a wave are split stream-K:
 //     their (row tile x k step) units are divided evenly and contiguously over the CTAs; partially covered tiles
 //     go to a workspace and a tiny fixup kernel adds them in a fixed order (bit-reproducible, no atomics).
-//     DAV_MATVEC_SCHEDULE=0 selects pure stream-K (every CTA at a different k position).
+//     Pure stream-K (every CTA at a different k position) is used for blocks of up to 32 columns; see schedule_for().
 //   * warp-specialised: warp 8 is the TMA producer, warps 0-7 consume (each 32 rows x up to 32 columns).  A tiles arrive through a
 //     2D tensor map (box 16 rows x 16 columns, 128-byte swizzle) with mbarrier complete_tx; the X
 //     tile is pre-packed in fragment order so one 1D bulk copy per stage fetches it.
@@ -38,7 +38,6 @@ constexpr int CONSUMERS = 8;      // consumer warps
 constexpr int THREADS = (CONSUMERS + 1) * 32;
 constexpr int MAX_STAGES = 8;
 constexpr int NUM_SMS_FALLBACK = 148;
-constexpr int MATVEC_SCHEDULE_DEFAULT = 0;  // see the header comment; DAV_MATVEC_SCHEDULE overrides
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -524,10 +523,15 @@ static int bk_from_env() {
   return (v == 16 || v == 32) ? v : BK_DEFAULT;
 }
 
-static int schedule_from_env() {
-  // 1: full waves + stream-K remainder; 0: pure stream-K.  Read per call so one process can compare the two.
+// 0: pure stream-K, 1: full waves + stream-K remainder, 2: full waves + aligned split-K remainder.  DAV_MATVEC_SCHEDULE
+// overrides (read per call so one process can compare them).  Default: waves for blocks wider than 32 columns, where
+// the packed X block (n x b doubles, 51 MB at n = 100,000, b = 64) no longer stays in L2 next to the A stream when the
+// 148 CTAs of stream-K sit at 148 different k positions -- ncu at n = 100,000: DRAM reads 105-110 GB -> 81.7 GB at b = 64,
+// 142 GB -> 84.3 GB at b = 128 (algorithmic 80.1 / 80.2 GB), same kernel time; stream-K for the narrow, HBM-bound blocks
+// (reads already 80.0 / 81.0 GB at b = 16 / 32).
+static int schedule_for(int bpad) {
   const char* e = std::getenv("DAV_MATVEC_SCHEDULE");
-  return e ? std::atoi(e) : MATVEC_SCHEDULE_DEFAULT;
+  return e ? std::atoi(e) : (bpad > 32 ? 1 : 0);
 }
 
 // Host model of the schedule the kernels execute (same inline functions): enumerates the segments of every CTA and
@@ -542,7 +546,7 @@ int matvec_schedule_selftest(int64_t M, int64_t K, int b, int num_sms, int sched
   const int tiles = (int)ceil_div(M, (int64_t)BM);
   const int BK = bk_from_env();
   const int ksteps = (int)(round_up(K, BK) / BK);
-  if (schedule < 0) schedule = schedule_from_env();
+  if (schedule < 0) schedule = schedule_for(bpad);
   const Sched sc = make_sched(tiles, ksteps, num_sms, schedule);
   if (sc.grid < 1 || sc.grid > num_sms) return 1;
   if ((long long)tiles * ksteps > (1LL << 28)) return -2;  // the coverage map below is meant for test sizes
@@ -668,7 +672,7 @@ void matvec_dmma(cudaStream_t s, MatvecPlan* plan, int b, const double* X, int64
       static const int hints = [] { const char* e = std::getenv("DAV_MATVEC_L2_HINTS"); return e ? std::atoi(e) : 2; }();
       p.l2_hints = hints;
     }
-    const int schedule = schedule_from_env();
+    const int schedule = schedule_for(bpad);
 #define CFG(NT_, WN_)                                                                                          \
   do {                                                                                                         \
     if (BK == 32)                                                                                              \
