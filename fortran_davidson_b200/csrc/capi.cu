@@ -156,6 +156,41 @@ int dav_bench_fp64_pipe(dav_solver_t* h, int reps, double* dmma_tflops) {
   API_END
 }
 
+int dav_debug_matvec_rect(int device, int64_t m, int64_t k, int b, double* max_abs_diff, double* scale) {
+  API_BEGIN
+  need(m >= 1 && k >= 1 && b >= 1 && b <= 128 && max_abs_diff && scale, "bad arguments");
+  CK(cudaSetDevice(device));
+  Ctx c;
+  const int64_t lda = round_up(m, 16);
+  DevBuf<double> A, X, W1, W2;
+  A.alloc((size_t)lda * k); X.alloc((size_t)k * b); W1.alloc((size_t)m * b); W2.alloc((size_t)m * b);
+  fill_random(c.s, A.p, (size_t)lda * k, 0xA11CEULL);
+  fill_random(c.s, X.p, (size_t)k * b, 0xB0BULL);
+  MatvecPlan* plan = matvec_plan_create(A.p, m, k, lda, b);
+  try {
+    matvec_dmma(c.s, plan, b, X.p, k, W1.p, m);
+    gemm(c.s, false, m, b, k, 1.0, A.p, lda, X.p, k, 0.0, W2.p, m, nullptr, 0);
+    c.sync();
+  } catch (...) {
+    matvec_plan_destroy(plan);
+    throw;
+  }
+  matvec_plan_destroy(plan);
+  std::vector<double> h1((size_t)m * b), h2((size_t)m * b);
+  d2h(h1.data(), W1.p, h1.size(), c.s);
+  d2h(h2.data(), W2.p, h2.size(), c.s);
+  c.sync();
+  double d = 0.0, sc = 0.0;
+  for (size_t i = 0; i < h1.size(); ++i) {
+    const double e = std::fabs(h1[i] - h2[i]);
+    if (!(e <= d)) d = e;  // NaN-propagating maximum
+    sc = std::max(sc, std::fabs(h2[i]));
+  }
+  *max_abs_diff = d;
+  *scale = sc;
+  API_END
+}
+
 int dav_debug_matvec_schedule(int64_t m, int64_t k, int b, int num_sms, int schedule, long long* info) {
   API_BEGIN
   const int rc = matvec_schedule_selftest(m, k, b, num_sms, schedule, info);

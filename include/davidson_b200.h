@@ -186,6 +186,13 @@ int dav_bench_block_matvec(dav_solver_t* h, int which, int64_t b, int reps, floa
  * registers on every SM, best of `reps` launches of ~2 ms.  Denominator of the FP64 roofline in bench.py. */
 int dav_bench_fp64_pipe(dav_solver_t* h, int reps, double* dmma_tflops);
 
+/* Device self-check of the block matvec on a RECTANGULAR m x k block (the shape of a rank's row block in the sharded
+ * solve: m = n / ranks rows, k = n columns): pseudo-random A and X generated on the device, W = A X by the TMA/DMMA
+ * kernel (schedule / stage depth as DAV_MATVEC_SCHEDULE / DAV_MATVEC_BK or the defaults select) against the
+ * tall-skinny GEMM kernel of the library; returns max |W_matvec - W_gemm| and max |W_gemm|.  Lets one GPU validate the
+ * multi-GPU tile shapes. */
+int dav_debug_matvec_rect(int device, int64_t m, int64_t k, int b, double* max_abs_diff, double* scale);
+
 /* Host-only check of the block-matvec work schedule (full waves + stream-K remainder) for an M x K local block and
  * a b-column block on a device with num_sms SMs: runs the very functions the kernel and its fixup pass use and
  * verifies that every (row tile, k step) unit is computed exactly once and every partial tile is summed exactly

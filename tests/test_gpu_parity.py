@@ -129,6 +129,25 @@ def test_block_matvec_schedules(n, b, uploaded, monkeypatch):
             assert np.abs(W[v] - ref).max() <= 1e-12 * np.abs(ref).max(), v
 
 
+@pytest.mark.parametrize("m,k,b", [(50000, 100000, 64), (25000, 100000, 128), (12544, 100000, 64), (12192, 100000, 16),
+                                   (19000, 30000, 100)])
+def test_block_matvec_rectangular_row_blocks(m, k, b, monkeypatch):
+    """The row blocks of the sharded solve are rectangular (m = rows of a rank, k = n): TMA/DMMA matvec under every
+    schedule against the library's tall-skinny GEMM on device-generated data (one GPU validates the multi-GPU tiles)."""
+    import ctypes as C
+    L = fd.lib()
+    L.dav_debug_matvec_rect.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_double),
+                                        C.POINTER(C.c_double)]
+    for sched in (None, "0", "1", "2"):
+        if sched is None:
+            monkeypatch.delenv("DAV_MATVEC_SCHEDULE", raising=False)
+        else:
+            monkeypatch.setenv("DAV_MATVEC_SCHEDULE", sched)
+        d, s = C.c_double(), C.c_double()
+        assert L.dav_debug_matvec_rect(0, m, k, b, C.byref(d), C.byref(s)) == 0, L.dav_last_error()
+        assert s.value > 1.0 and d.value <= 1e-11 * s.value, (sched, d.value, s.value)
+
+
 def test_block_matvec_linearity_large():
     """Size-independent property at a size the oracle would not finish quickly: A(x+2y) == Ax + 2Ay and
     device-generated A equals the oracle's stream on a sampled sub-block."""
