@@ -98,3 +98,45 @@ def test_package_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f
+
+
+def test_text_dump_format_roundtrip(tmp_path):
+    """write_vector / write_matrix / read_matrix of the reference's test helper (tests/test_utils.f90:118-167): one value
+    per line, row-major traversal, readable by np.loadtxt the way test_davidson.py / test_lapack.py read the dumps."""
+    from fortran_davidson_b200 import test_utils as tu
+    rng = np.random.default_rng(3)
+    m = np.asfortranarray(rng.standard_normal((7, 5)))
+    p = str(tmp_path / "m.txt")
+    tu.write_matrix(p, m)
+    flat = np.loadtxt(p)
+    assert flat.shape == (35,) and np.array_equal(flat.reshape(7, 5), m)  # row-major, full precision
+    v = rng.standard_normal(9)
+    tu.write_vector(p, v)
+    assert np.array_equal(np.loadtxt(p), v)
+    sq = np.asfortranarray(rng.standard_normal((6, 6)))
+    tu.write_matrix(p, sq)
+    assert np.array_equal(tu.read_matrix(p, 6), sq)
+    # the reference's own fixture: 100 rows of 100 list-directed values (src/tests/matrix.txt -> tests/golden/matrix_100.npy)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "matrix_100.npy"))
+    with open(p, "w") as fh:
+        for i in range(100):
+            fh.write(" ".join("%.17g" % x for x in g[i]) + "\n")
+    assert np.array_equal(tu.read_matrix(p, 100), g)
+    with pytest.raises(ValueError):
+        tu.read_matrix(p, 99)
+
+
+def test_example_programs_compile():
+    """The example programs (the reference's main / benchmark / test programs on the mirror) are at least valid Python
+    that imports only the package (they run on the GPU box: tests/test_reference_harness.py)."""
+    import ast
+    ex = os.path.join(ROOT, "examples")
+    names = sorted(f for f in os.listdir(ex) if f.endswith(".py"))
+    assert {"main.py", "benchmark_free.py", "test_dense_numpy.py", "test_free_numpy.py", "test_call_lapack.py",
+            "test_dense_properties.py", "test_free_properties.py"} <= set(names)
+    for f in names:
+        tree = ast.parse(open(os.path.join(ex, f)).read(), f)
+        for node in ast.walk(tree):
+            if isinstance(node, (ast.Import, ast.ImportFrom)):
+                mod = node.module if isinstance(node, ast.ImportFrom) else node.names[0].name
+                assert not (mod or "").startswith("oracle"), f
