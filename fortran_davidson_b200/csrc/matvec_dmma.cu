@@ -4,16 +4,18 @@
 // iteration (davidson.f90:163-170).
 //
 // sm_100a design
-//   * persistent grid, one CTA per SM.  Schedule = full WAVES + a stream-K remainder: while at least `grid` row
-//     tiles are left, CTA c takes tile (wave*grid + c) and all CTAs sweep the k steps together, so at any moment
-//     the whole grid reads the same ~16 columns of A (contiguous in HBM over the row tiles, the same few 2 MB
-//     pages for every SM, one X tile shared through L2).  The tiles that do not fill a wave are split stream-K:
-//     their (row tile x k step) units are divided evenly and contiguously over the CTAs; partially covered tiles
-//     go to a workspace and a tiny fixup kernel adds them in a fixed order (bit-reproducible, no atomics).
-//     Pure stream-K (every CTA at a different k position) is used for blocks of up to 32 columns; see schedule_for().
-//   * warp-specialised: warp 8 is the TMA producer, warps 0-7 consume (each 32 rows x up to 32 columns).  A tiles arrive through a
-//     2D tensor map (box 16 rows x 16 columns, 128-byte swizzle) with mbarrier complete_tx; the X
-//     tile is pre-packed in fragment order so one 1D bulk copy per stage fetches it.
+//   * persistent grid, one CTA per SM.  Blocks of up to 32 columns (HBM- or just FP64-bound): stream-K -- the
+//     (row tile x k step) units are divided evenly and contiguously over the CTAs; partially covered tiles go to a
+//     workspace and a tiny fixup kernel adds them in increasing-k order (bit-reproducible, no atomics).  Wider
+//     blocks: full WAVES + a stream-K remainder -- while at least `grid` row tiles are left, CTA c takes tile
+//     (wave*grid + c) and all CTAs sweep the k steps together, so one X tile serves the whole grid from L2 instead
+//     of all of X (51 MB at n = 100,000, b = 64) staying live next to the A stream; same kernel time, DRAM reads
+//     back to the algorithmic 80 GB (see schedule_for()).
+//   * warp-specialised: warp 8 is the TMA producer, warps 0-7 consume (each 32 rows x up to 32 columns).  A tiles
+//     arrive through a 2D tensor map (boxes of 16 rows x BK = 32 columns, 128-byte swizzle) with mbarrier
+//     complete_tx; the X tile is pre-packed in fragment order so one 1D bulk copy per stage fetches it.  The slot
+//     hand-back crosses memory proxies (ld.shared reads, async-proxy refill): block fence before the consumers'
+//     arrive, fence.proxy.async before the producer's TMA issue.
 //   * FP64 tensor-core math: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4).  tcgen05 has no FP64 kind, so
 //     TMEM / UTCMMA do not apply to this path.
 //   * shared-memory fragment loads are 128-bit and bank-conflict free: the 128B swizzle puts rows
