@@ -372,6 +372,8 @@ def main():
                          "gather_new_block": st.gather_ms, "output_vectors": st.output_ms,
                          "nccl_inside_phases": st.comm_ms},
             "collectives_per_solve": int(st.collectives),
+            "transport": (("peer-memory kernels (cudaIpc-mapped NVLink stores, csrc/comm.cu)" if solver.comm_info()["peer"]
+                           else "NCCL") if distributed else "single GPU"),
             "gpu_launches": int(sum(launches) / len(launches)), "matvec_launches": int(mv_launch[-1]),
             "clocks": clocks.summary(), "roofline": roofline}
 

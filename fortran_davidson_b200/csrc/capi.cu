@@ -368,6 +368,25 @@ int dav_bench_block_matvec(dav_solver_t* h, int which, int64_t b, int reps, floa
   API_END
 }
 
+int dav_debug_collective(dav_solver_t* h, int kind, int64_t count, int reps, double* out2) {
+  API_BEGIN
+  need(h && out2, "bad handle / output");
+  CK(cudaSetDevice(h->device));
+  need(h->comm.active(), "dav_debug_collective needs a distributed handle");
+  need(kind <= 1 || h->n > 0, "set a matrix first (the gathers use the handle's row partition)");
+  h->comm.debug_exchange(kind, count, reps, h->n, h->nl, h->row0, h->stream, out2);
+  API_END
+}
+
+int dav_comm_info(dav_solver_t* h, int* peer_transport, long long* peer_calls, long long* nccl_calls) {
+  API_BEGIN
+  need(h, "bad handle");
+  if (peer_transport) *peer_transport = h->comm.peer() ? 1 : 0;
+  if (peer_calls) *peer_calls = h->comm.peer_calls;
+  if (nccl_calls) *nccl_calls = h->comm.nccl_calls;
+  API_END
+}
+
 // ---------------------------------------------------------------------------------------------
 // drop-in solver calls
 // ---------------------------------------------------------------------------------------------

@@ -2,8 +2,12 @@
 
 #include <dlfcn.h>
 
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
+
+#include "kernels.cuh"
 
 namespace dav {
 namespace {
@@ -60,7 +64,286 @@ void check(ncclResult_t r, const char* what) {
   if (r != 0) DAV_THROW(DAV_ERR_COMM, "NCCL %s failed: %s", what, api().GetErrorString ? api().GetErrorString(r) : "?");
 }
 
+// ---- device side of the peer transport ------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// waits until *flag >= epoch; gives up after ~4 s (a peer died) and records it, so that a broken job ends with an
+// error instead of hanging the GPU
+__device__ __forceinline__ void wait_flag(const unsigned long long* flag, unsigned long long epoch, int* error) {
+  if (ld_acquire_sys(flag) >= epoch) return;
+  const unsigned long long t0 = globaltimer_ns();
+  unsigned spins = 0;
+  while (ld_acquire_sys(flag) < epoch) {
+    if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > 4000000000ULL) {
+      *error = 1;
+      return;
+    }
+  }
+}
+
+// all CTAs have issued (and fenced) their peer stores -> the last one to arrive returns true
+__device__ __forceinline__ bool last_cta_arrives(unsigned int* counter) {
+  __shared__ int is_last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(counter, 1u);
+    is_last = (prev == gridDim.x - 1);
+    if (is_last) *counter = 0;  // every other CTA has already passed its atomicAdd
+    __threadfence();
+  }
+  __syncthreads();
+  return is_last != 0;
+}
+
+// One-shot all-reduce.  slot layout on every rank: [parity][source rank][cap].  Two parities: a rank can start
+// all-reduce e+1 (storing into parity (e+1)&1) while a slower peer still adds the slots of e, but not e+2 -- that
+// needs the peer's flag for e+1, which the peer raises only after it has finished reading e (stream order).
+// gather_out != nullptr: no sum, a small all-gather of two segments: words [0, seg) of rank p go to
+// gather_out[p * seg + i], words [seg, count) behind all first segments (seg == count: plain all-gather).
+__global__ void __launch_bounds__(256) peer_allreduce_kernel(PeerArgs a, double* __restrict__ buf, size_t count,
+                                                             size_t cap, unsigned long long epoch,
+                                                             double* __restrict__ gather_out, size_t seg) {
+  const int P = a.world, r = a.rank;
+  const size_t par = (size_t)(epoch & 1ULL) * (size_t)P * cap;
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gs = (size_t)gridDim.x * blockDim.x;
+  PeerCtl* me = a.ctl[r];
+  for (size_t i = gt; i < count; i += gs) {
+    const double v = buf[i];
+#pragma unroll 4
+    for (int p = 0; p < P; ++p) a.data[p][par + (size_t)r * cap + i] = v;
+  }
+  if (last_cta_arrives(&me->counter[0])) {
+    if ((int)threadIdx.x < P) {
+      __threadfence_system();
+      st_release_sys(&a.ctl[threadIdx.x]->ar_flag[r], epoch);
+    }
+  }
+  if ((int)threadIdx.x < P) wait_flag(&me->ar_flag[threadIdx.x], epoch, &me->error);
+  __syncthreads();
+  const double* mine = a.data[r] + par;
+  if (gather_out) {
+    for (size_t i = gt; i < count; i += gs)
+      for (int p = 0; p < P; ++p) {
+        const size_t o = i < seg ? (size_t)p * seg + i : (size_t)P * seg + (size_t)p * (count - seg) + (i - seg);
+        gather_out[o] = __ldcg(mine + (size_t)p * cap + i);
+      }
+    return;
+  }
+  for (size_t i = gt; i < count; i += gs) {
+    double s = 0.0;
+    for (int p = 0; p < P; ++p) s += __ldcg(mine + (size_t)p * cap + i);  // rank order: identical on every rank
+    buf[i] = s;
+  }
+}
+
+// gather, shared prologue / epilogue.  Prologue = barrier: nobody stores into a peer's block before that peer's
+// stream has reached its own gather call (all its readers of the previous block are complete by stream order).
+__device__ __forceinline__ void gather_prologue(const PeerArgs& a, unsigned long long epoch) {
+  const int P = a.world, r = a.rank;
+  PeerCtl* me = a.ctl[r];
+  if (blockIdx.x == 0 && (int)threadIdx.x < P) st_release_sys(&a.ctl[threadIdx.x]->ag_ready[r], epoch);
+  if ((int)threadIdx.x < P) wait_flag(&me->ag_ready[threadIdx.x], epoch, &me->error);
+  __syncthreads();
+}
+__device__ __forceinline__ void gather_epilogue(const PeerArgs& a, unsigned long long epoch) {
+  const int P = a.world, r = a.rank;
+  PeerCtl* me = a.ctl[r];
+  if (last_cta_arrives(&me->counter[1])) {
+    if ((int)threadIdx.x < P) {
+      __threadfence_system();
+      st_release_sys(&a.ctl[threadIdx.x]->ag_done[r], epoch);
+      wait_flag(&me->ag_done[threadIdx.x], epoch, &me->error);
+    }
+  }
+}
+
+// dst(row0 + i, j) on every rank <- X(i, j); dst column-major with leading dimension n
+__global__ void __launch_bounds__(256) peer_gather_rows_kernel(PeerArgs a, const double* __restrict__ X, int64_t ldx,
+                                                               int64_t nl, int64_t row0, int64_t n, int b,
+                                                               unsigned long long epoch) {
+  gather_prologue(a, epoch);
+  const int P = a.world;
+  const int64_t total = nl * b;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = e / nl, i = e - j * nl;
+    const double v = X[i + j * ldx];
+    const int64_t o = row0 + i + j * n;
+#pragma unroll 4
+    for (int p = 0; p < P; ++p) a.data[(a.rank + p) % P][o] = v;  // start with myself, peers staggered
+  }
+  gather_epilogue(a, epoch);
+}
+
+// the same into the packed fragment order (see comm.cuh); this rank owns rows [row0, row1) of the padded range
+// [0, Kpad): row1 = row0 + nl, except that the last rank also zero-fills K..Kpad.  One thread per 16-byte pair
+// (k, k+1) of the packed layout: coalesced 16-byte peer stores.
+__global__ void __launch_bounds__(256)
+    peer_gather_packed_kernel(PeerArgs a, const double* __restrict__ X, int64_t ldx, int64_t nl, int64_t row0,
+                              int64_t row_end /* row0 + nl, or Kpad on the last rank */, int64_t Kpad, int b,
+                              int nchunks, unsigned long long epoch) {
+  gather_prologue(a, epoch);
+  const int P = a.world;
+  const int64_t kq0 = row0 >> 3, nkq = (row_end - row0 + 7) >> 3;  // row0 is a multiple of 8
+  for (int c = 0; c < nchunks; ++c) {
+    const int c0 = c * 128;
+    const int bc = min(128, b - c0);
+    const int bp = ((bc + 7) / 8) * 8;  // same rule as matvec_bpad()
+    const int warps_n = bp <= 32 ? 1 : (bp <= 64 ? 2 : 4);
+    int nt = (bp + 8 * warps_n - 1) / (8 * warps_n);
+    if (warps_n > 1 && nt < 3) nt = 3;
+    const int ntt = nt * warps_n;  // 8-column tiles of the chunk (bpad = 8 * ntt)
+    const int64_t base = (int64_t)c0 * Kpad;
+    // pairs: per k-group of 8 rows: ntt tiles x 8 columns x 4 row pairs
+    const int64_t per_kq = (int64_t)ntt * 32;
+    const int64_t total = nkq * per_kq;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t kq = e / per_kq;
+      const int rem = (int)(e - kq * per_kq);
+      const int jt = rem >> 5, g = (rem >> 2) & 7, kp = rem & 3;
+      const int j = c0 + jt * 8 + g;
+      const int64_t k = (kq0 + kq) * 8 + 2 * kp;
+      double2 v = make_double2(0.0, 0.0);
+      if (j < b) {
+        const int64_t i = k - row0;
+        if (i < nl) v.x = X[i + (int64_t)j * ldx];
+        if (i + 1 < nl) v.y = X[i + 1 + (int64_t)j * ldx];
+      }
+      const int64_t o = base + ((kq0 + kq) * ntt + jt) * 64 + g * 8 + 2 * kp;
+#pragma unroll 4
+      for (int p = 0; p < P; ++p) *reinterpret_cast<double2*>(a.data[(a.rank + p) % P] + o) = v;
+    }
+  }
+  gather_epilogue(a, epoch);
+}
+
+// ---- self-checks (dav_debug_collective) --------------------------------------------------------------------------
+__device__ __forceinline__ double dbg_value(int64_t row, int64_t col) {
+  return (double)((row * 131 + col * 7919) % 1000003) * 1e-3 + 1.0;
+}
+__global__ void dbg_fill_rows_kernel(double* X, int64_t ld, int64_t nl, int64_t row0, int b) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nl * b; e += (int64_t)gridDim.x * blockDim.x)
+    X[e % nl + (e / nl) * ld] = dbg_value(row0 + e % nl, e / nl);
+}
+__global__ void dbg_fill_vec_kernel(double* x, int64_t count, int rank) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x)
+    x[e] = (double)(rank + 1) + 1e-3 * (double)(e % 4096);
+}
+// err[0] = max |got - expected| (atomicMax on the bit pattern of a non-negative double)
+__device__ __forceinline__ void dbg_max(double* err, double d) {
+  atomicMax((unsigned long long*)err, (unsigned long long)__double_as_longlong(fabs(d)));
+}
+__global__ void dbg_check_vec_kernel(const double* x, int64_t count, int world, double* err) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int r = 0; r < world; ++r) s += (double)(r + 1) + 1e-3 * (double)(e % 4096);
+    dbg_max(err, x[e] - s);
+  }
+}
+__global__ void dbg_check_full_kernel(const double* X, int64_t n, int b, double* err) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n * b; e += (int64_t)gridDim.x * blockDim.x)
+    dbg_max(err, X[e] - dbg_value(e % n, e / n));
+}
+__global__ void dbg_check_packed_kernel(const double* Xp, int64_t n, int64_t Kpad, int b, double* err) {
+  const int nchunks = (b + 127) / 128;
+  for (int c = 0; c < nchunks; ++c) {
+    const int c0 = c * 128, bc = min(128, b - c0);
+    const int bp = ((bc + 7) / 8) * 8;
+    const int warps_n = bp <= 32 ? 1 : (bp <= 64 ? 2 : 4);
+    int nt = (bp + 8 * warps_n - 1) / (8 * warps_n);
+    if (warps_n > 1 && nt < 3) nt = 3;
+    const int ntt = nt * warps_n, bpad = ntt * 8;
+    const int64_t total = Kpad * bpad;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+      const int kk = (int)(e & 7), g = (int)((e >> 3) & 7);
+      const int64_t blk = e >> 6;
+      const int jt = (int)(blk % ntt);
+      const int64_t k = (blk / ntt) * 8 + kk;
+      const int j = c0 + jt * 8 + g;
+      const double expect = (k < n && j < b) ? dbg_value(k, j) : 0.0;
+      dbg_max(err, Xp[(int64_t)c0 * Kpad + e] - expect);
+    }
+  }
+}
+
 }  // namespace
+
+void Comm::debug_exchange(int kind, int64_t count, int reps, int64_t n, int64_t nl, int64_t row0, cudaStream_t s,
+                          double* out) {
+  if (world_ <= 1) DAV_THROW(DAV_ERR_STATE, "debug_exchange needs more than one rank");
+  if (kind < 0 || kind > 3 || count < 1 || reps < 1) DAV_THROW(DAV_ERR_INVALID, "debug_exchange: bad arguments");
+  DevBuf<double> x, err;
+  err.alloc(1);
+  CK(cudaMemsetAsync(err.p, 0, 8, s));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  SymBuf dst;
+  if (kind <= 1) {
+    reserve_allreduce((size_t)count, s);
+    x.alloc((size_t)count);
+    for (int r = 0; r <= reps; ++r) {  // r == 0: warm-up + correctness
+      if (r == 1) CK(cudaEventRecord(e0, s));
+      if (r <= 1) dbg_fill_vec_kernel<<<64, 256, 0, s>>>(x.p, count, rank_);
+      if (kind == 0) allreduce_sum(x.p, (size_t)count, s);
+      else nccl_allreduce(x.p, (size_t)count, s);
+      if (r == 0) dbg_check_vec_kernel<<<64, 256, 0, s>>>(x.p, count, world_, err.p);
+    }
+  } else {
+    if (!peer_) reserve_allreduce(1, s);
+    if (!peer_) DAV_THROW(DAV_ERR_STATE, "debug_exchange: the peer transport is not available");
+    const int b = (int)count;
+    const int64_t Kpad = matvec_kpad(n);
+    x.alloc((size_t)std::max<int64_t>(nl, 1) * b);
+    sym_reserve(dst, std::max((size_t)n * b, matvec_packed_doubles(n, b)) * 8, s);
+    dbg_fill_rows_kernel<<<128, 256, 0, s>>>(x.p, std::max<int64_t>(nl, 1), nl, row0, b);
+    for (int r = 0; r <= reps; ++r) {
+      if (r == 1) CK(cudaEventRecord(e0, s));
+      if (kind == 2) gather_rows(x.p, std::max<int64_t>(nl, 1), nl, row0, n, b, dst, s);
+      else gather_rows_packed(x.p, std::max<int64_t>(nl, 1), nl, row0, n, Kpad, b, dst, s);
+      if (r == 0) {
+        if (kind == 2) dbg_check_full_kernel<<<256, 256, 0, s>>>(dst.p(), n, b, err.p);
+        else dbg_check_packed_kernel<<<256, 256, 0, s>>>(dst.p(), n, Kpad, b, err.p);
+      }
+    }
+  }
+  CK(cudaEventRecord(e1, s));
+  CK(cudaStreamSynchronize(s));
+  CK_LAUNCH();
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  double herr = 0.0;
+  CK(cudaMemcpy(&herr, err.p, 8, cudaMemcpyDeviceToHost));
+  int perr = 0;
+  if (error_flag()) CK(cudaMemcpy(&perr, error_flag(), sizeof(int), cudaMemcpyDeviceToHost));
+  if (dst.local) sym_release(dst);
+  if (perr) DAV_THROW(DAV_ERR_COMM, "a wait inside a peer exchange kernel timed out");
+  out[0] = 1e3 * (double)ms / reps;
+  out[1] = herr;
+}
+
+int matvec_bpad(int bc) {
+  int bp = (int)round_up(bc, 8);
+  const int warps_n = bp <= 32 ? 1 : (bp <= 64 ? 2 : 4);
+  int nt = (bp + 8 * warps_n - 1) / (8 * warps_n);
+  if (warps_n > 1 && nt < 3) nt = 3;
+  return nt * warps_n * 8;
+}
 
 void Comm::get_unique_id(void* id128) {
   Api& a = api();
@@ -74,6 +357,7 @@ void Comm::init(int rank, int world, const void* id128) {
   rank_ = rank;
   world_ = world;
   if (world <= 1) return;
+  if (world > COMM_MAX_RANKS) DAV_THROW(DAV_ERR_INVALID, "at most %d ranks are supported", COMM_MAX_RANKS);
   Api& a = api();
   if (!a.ok) DAV_THROW(DAV_ERR_COMM, "NCCL unavailable: %s", a.why.c_str());
   NcclUniqueId id;
@@ -84,20 +368,206 @@ void Comm::init(int rank, int world, const void* id128) {
 }
 
 Comm::~Comm() {
+  if (peer_ || ctl_.local || slots_.local) {
+    sym_release(slots_);
+    sym_release(ctl_);
+  }
+  if (hbuf_) cudaFree(hbuf_);
   if (comm_) api().CommDestroy((ncclComm_t)comm_);
+}
+
+// ---- symmetric segments ----------------------------------------------------------------------------------------
+// Collective.  Exchanges (handle, ok) of every rank with one ncclAllGather; the peer transport is used only if the
+// mapping worked on EVERY rank (the decision is part of the exchanged data, so all ranks take the same branch).
+void Comm::sym_reserve(SymBuf& b, size_t bytes, cudaStream_t s) {
+  if (world_ <= 1) return;
+  bytes = (size_t)round_up((int64_t)std::max<size_t>(bytes, 256), 256);
+  if (b.local && b.bytes >= bytes) return;
+  sym_release(b);
+  struct Rec { cudaIpcMemHandle_t h; int ok; int pad[15]; };
+  static_assert(sizeof(Rec) == 128, "record size");
+  Rec mine;
+  std::memset(&mine, 0, sizeof(mine));
+  void* ptr = nullptr;
+  cudaError_t e = cudaMalloc(&ptr, bytes);
+  if (e != cudaSuccess) DAV_THROW(DAV_ERR_CUDA, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+  CK(cudaMemsetAsync(ptr, 0, bytes, s));
+  mine.ok = cudaIpcGetMemHandle(&mine.h, ptr) == cudaSuccess;
+  (void)cudaGetLastError();
+  if (!hbuf_) CK(cudaMalloc(&hbuf_, sizeof(Rec) * (COMM_MAX_RANKS + 1)));
+  Rec* dsend = (Rec*)hbuf_;
+  Rec* drecv = dsend + 1;
+  std::vector<Rec> all((size_t)world_);
+  auto exchange = [&]() {
+    CK(cudaMemcpyAsync(dsend, &mine, sizeof(Rec), cudaMemcpyHostToDevice, s));
+    check(api().AllGather(dsend, drecv, sizeof(Rec), NCCL_UINT8, (ncclComm_t)comm_, s), "ncclAllGather");
+    CK(cudaMemcpyAsync(all.data(), drecv, sizeof(Rec) * world_, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  };
+  exchange();
+  bool ok = true;
+  for (int r = 0; r < world_; ++r) ok = ok && all[(size_t)r].ok;
+  b.local = ptr;
+  b.bytes = bytes;
+  b.peer[rank_] = ptr;
+  if (ok) {
+    for (int r = 0; r < world_ && ok; ++r) {
+      if (r == rank_) continue;
+      void* q = nullptr;
+      if (cudaIpcOpenMemHandle(&q, all[(size_t)r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        (void)cudaGetLastError();
+        ok = false;
+      } else {
+        b.peer[r] = q;
+      }
+    }
+  }
+  // second round: did every rank manage to map every peer?
+  mine.ok = ok;
+  exchange();
+  bool all_ok = true;
+  for (int r = 0; r < world_; ++r) all_ok = all_ok && all[(size_t)r].ok;
+  if (!all_ok) {
+    for (int r = 0; r < world_; ++r)
+      if (r != rank_ && b.peer[r]) {
+        cudaIpcCloseMemHandle(b.peer[r]);
+        b.peer[r] = nullptr;
+      }
+    DAV_THROW(DAV_ERR_COMM, "peer mapping (cudaIpc) of a %zu-byte segment failed on some rank", bytes);
+  }
+}
+
+void Comm::sym_release(SymBuf& b) {
+  if (!b.local) return;
+  cudaDeviceSynchronize();
+  for (int r = 0; r < world_; ++r)
+    if (r != rank_ && b.peer[r]) cudaIpcCloseMemHandle(b.peer[r]);
+  // nobody may unmap-and-free while a peer still has stores in flight towards this segment: every rank has
+  // synchronised its device above; one small NCCL all-reduce is the barrier between "all closed" and "free"
+  if (comm_ && hbuf_) {
+    if (api().AllReduce(hbuf_, hbuf_, 1, NCCL_FLOAT64, NCCL_SUM, (ncclComm_t)comm_, (cudaStream_t)0) == 0)
+      cudaDeviceSynchronize();
+  }
+  cudaFree(b.local);
+  b = SymBuf();
+}
+
+void Comm::setup_peer(cudaStream_t s) {
+  if (peer_tried_) return;
+  peer_tried_ = true;
+  peer_ = false;
+  if (world_ <= 1) return;
+  const char* env = std::getenv("DAV_PEER_COLLECTIVES");
+  if (env && std::atoi(env) == 0) return;
+  try {
+    sym_reserve(ctl_, sizeof(PeerCtl), s);
+    peer_ = true;
+  } catch (const Error&) {
+    if (env && std::atoi(env) == 1) throw;  // forced: fail loudly
+    peer_ = false;
+  }
+}
+
+PeerArgs Comm::args_for(const SymBuf& b) const {
+  PeerArgs a;
+  std::memset(&a, 0, sizeof(a));
+  for (int r = 0; r < world_; ++r) {
+    a.data[r] = (double*)b.peer[r];
+    a.ctl[r] = (PeerCtl*)ctl_.peer[r];
+  }
+  a.rank = rank_;
+  a.world = world_;
+  return a;
+}
+
+void Comm::reserve_allreduce(size_t max_count, cudaStream_t s) {
+  if (world_ <= 1) return;
+  setup_peer(s);
+  if (!peer_) return;
+  if (max_count <= slot_cap_) return;
+  const size_t cap = (size_t)round_up((int64_t)max_count, 32);
+  sym_reserve(slots_, 2 * (size_t)world_ * cap * sizeof(double), s);
+  slot_cap_ = cap;
+}
+
+void Comm::nccl_allreduce(double* buf, size_t count, cudaStream_t s) {
+  check(api().AllReduce(buf, buf, count, NCCL_FLOAT64, NCCL_SUM, (ncclComm_t)comm_, s), "ncclAllReduce");
+  ++nccl_calls;
 }
 
 void Comm::allreduce_sum(double* buf, size_t count, cudaStream_t s) {
   if (world_ <= 1 || count == 0) return;
-  check(api().AllReduce(buf, buf, count, NCCL_FLOAT64, NCCL_SUM, (ncclComm_t)comm_, s), "ncclAllReduce");
+  if (!peer_ || count > slot_cap_) {
+    nccl_allreduce(buf, count, s);
+    return;
+  }
+  ++ar_epoch_;
+  const int grid = (int)std::max<size_t>(1, std::min<size_t>((count + 511) / 512, 64));
+  peer_allreduce_kernel<<<grid, 256, 0, s>>>(args_for(slots_), buf, count, slot_cap_, ar_epoch_, nullptr, 0);
+  CK_LAUNCH();
+  ++g_kernel_launches;
+  ++peer_calls;
 }
 
 void Comm::allgather(const void* send, void* recv, size_t bytes_per_rank, cudaStream_t s) {
+  allgather2(send, recv, bytes_per_rank, 0, s);
+}
+
+void Comm::allgather2(const void* send, void* recv, size_t bytes_a, size_t bytes_b, cudaStream_t s) {
+  const size_t bytes = bytes_a + bytes_b;
   if (world_ <= 1) {
-    if (send != recv) CK(cudaMemcpyAsync(recv, send, bytes_per_rank, cudaMemcpyDeviceToDevice, s));
+    if (send != recv) CK(cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, s));
     return;
   }
-  check(api().AllGather(send, recv, bytes_per_rank, NCCL_UINT8, (ncclComm_t)comm_, s), "ncclAllGather");
+  if (peer_ && bytes_a % 8 == 0 && bytes_b % 8 == 0 && bytes / 8 <= slot_cap_ && ((uintptr_t)send & 7) == 0 &&
+      ((uintptr_t)recv & 7) == 0) {
+    // small payloads ride on the one-shot exchange (8-byte words, no arithmetic on them)
+    const size_t count = bytes / 8;
+    ++ar_epoch_;
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((count + 511) / 512, 64));
+    peer_allreduce_kernel<<<grid, 256, 0, s>>>(args_for(slots_), (double*)send, count, slot_cap_, ar_epoch_,
+                                               (double*)recv, bytes_a / 8);
+    CK_LAUNCH();
+    ++g_kernel_launches;
+    ++peer_calls;
+    return;
+  }
+  check(api().AllGather(send, recv, bytes_a, NCCL_UINT8, (ncclComm_t)comm_, s), "ncclAllGather");
+  ++nccl_calls;
+  if (bytes_b) {
+    check(api().AllGather((const char*)send + bytes_a, (char*)recv + bytes_a * world_, bytes_b, NCCL_UINT8,
+                          (ncclComm_t)comm_, s), "ncclAllGather");
+    ++nccl_calls;
+  }
+}
+
+void Comm::gather_rows(const double* Xlocal, int64_t ldx, int64_t nl, int64_t row0, int64_t n, int b, SymBuf& dst,
+                       cudaStream_t s) {
+  if (!peer_ || dst.bytes < (size_t)n * b * 8) DAV_THROW(DAV_ERR_STATE, "gather_rows: symmetric block not reserved");
+  ++ag_epoch_;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(nl * b, 1024), 128));
+  peer_gather_rows_kernel<<<grid, 256, 0, s>>>(args_for(dst), Xlocal, ldx, nl, row0, n, b, ag_epoch_);
+  CK_LAUNCH();
+  ++g_kernel_launches;
+  ++peer_calls;
+}
+
+void Comm::gather_rows_packed(const double* Xlocal, int64_t ldx, int64_t nl, int64_t row0, int64_t n, int64_t Kpad,
+                              int b, SymBuf& dst, cudaStream_t s) {
+  const int nchunks = (b + 127) / 128;
+  const size_t need = ((size_t)(nchunks - 1) * 128 + (size_t)matvec_bpad(b - (nchunks - 1) * 128)) * (size_t)Kpad * 8;
+  if (!peer_ || dst.bytes < need) DAV_THROW(DAV_ERR_STATE, "gather_rows_packed: symmetric block not reserved");
+  if (row0 % 8 != 0) DAV_THROW(DAV_ERR_STATE, "gather_rows_packed: row blocks must start at a multiple of 8");
+  ++ag_epoch_;
+  const bool last = row0 + nl >= n;
+  const int64_t row_end = last ? Kpad : row0 + nl;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div((row_end - row0) * matvec_bpad(std::min(b, 128)),
+                                                                         2048), 128));
+  peer_gather_packed_kernel<<<grid, 256, 0, s>>>(args_for(dst), Xlocal, ldx, nl, row0, row_end, Kpad, b, nchunks,
+                                                 ag_epoch_);
+  CK_LAUNCH();
+  ++g_kernel_launches;
+  ++peer_calls;
 }
 
 }  // namespace dav

@@ -34,6 +34,15 @@ void set_last_error(const std::string& s);
 
 #define CK_LAUNCH() CK(cudaGetLastError())
 
+// Per-DEVICE facts and one-time settings (a process may drive several GPUs: dav_create(h, device)).
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting of a kernel, so the "already done" mark
+// is kept per (kernel, device); both helpers are thread safe.
+int device_max_smem_optin();  // cudaDevAttrMaxSharedMemoryPerBlockOptin of the current device (cached per device)
+int device_num_sms();         // SM count of the current device (cached per device)
+void ensure_dyn_smem_impl(const void* func, int bytes);
+template <typename F>
+inline void ensure_dyn_smem(F* kernel, int bytes) { ensure_dyn_smem_impl((const void*)kernel, bytes); }
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 

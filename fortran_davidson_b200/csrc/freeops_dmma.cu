@@ -248,11 +248,7 @@ void launch_free(cudaStream_t s, FreeParams& p) {
   constexpr int BM = (8 / WARPS_N) * 32;
   constexpr int BPAD = NT * WARPS_N * 8;
   const size_t smem = 2 * (size_t)BM * 16 * 8 + 2 * (size_t)16 * BPAD * 8 + FSEG * FCOEF * 8 + 2 * KS * 16 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CK(cudaFuncSetAttribute(free_dmma_kernel<NT, WARPS_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  ensure_dyn_smem(free_dmma_kernel<NT, WARPS_N>, (int)smem);  // per (kernel, device)
   const unsigned grid = (unsigned)ceil_div(p.nl, BM);
   free_dmma_kernel<NT, WARPS_N><<<grid, 256, smem, s>>>(p);
   CK_LAUNCH();

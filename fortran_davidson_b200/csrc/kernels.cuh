@@ -24,6 +24,10 @@ void matvec_plan_destroy(MatvecPlan* p);
 bool matvec_dmma_supported();
 // X is K x b column-major (ldx); Xp is scratch for the packed copy of X (>= round_up(K,64)*round_up(b,8)).
 void matvec_dmma(cudaStream_t s, MatvecPlan* plan, int b, const double* X, int64_t ldx, double* W, int64_t ldw);
+// the same with X already in the packed fragment order (layout: comm.cuh, Comm::gather_rows_packed)
+int64_t matvec_kpad(int64_t K);                  // padded row count of the packed block
+size_t matvec_packed_doubles(int64_t K, int b);  // size of the packed block of b columns
+void matvec_dmma_packed(cudaStream_t s, MatvecPlan* plan, int b, const double* Xpacked, double* W, int64_t ldw);
 // host model of the (waves + stream-K) schedule the kernel executes; see matvec_dmma.cu.  0 = consistent.
 int matvec_schedule_selftest(int64_t M, int64_t K, int b, int num_sms, int schedule, long long* info);
 
@@ -84,8 +88,10 @@ void max_abs_dev(cudaStream_t s, int rows, int cols, const double* G, int64_t ld
 // Cholesky (upper, G = R^T R) in place on one CTA; status |= 2 when not positive definite
 void cholesky_upper(cudaStream_t s, int k, double* G, int64_t ld, int* status);
 // G (b x b, ld b, only read) = R^T R; T <- R^-1 (dense, upper).  flag[0] (device double) <- 1.0 if a pivot is not
-// safely positive, else 0.0.  Returns false (nothing launched) when b is too large for shared memory.
-bool chol_inv_upper(cudaStream_t s, int b, const double* G, double* T, double* flag);
+// safely positive, else 0.0.  Blocks too wide for shared memory (b >= ~170) use gwork (>= b*(b+1) doubles of global
+// scratch); returns false (nothing launched) only when that is needed and missing.
+bool chol_inv_upper(cudaStream_t s, int b, const double* G, double* T, double* flag, double* gwork = nullptr,
+                    size_t gwork_doubles = 0);
 // fused block orthonormalisation helpers (see solver.cu::orthonormalize_block_pip)
 void pip_prepare(cudaStream_t s, int k, int b, const double* Gall, const double* P, double* Gs, double* D,
                  double* metrics);

@@ -491,11 +491,7 @@ void launch_cfg(cudaStream_t s, const CUtensorMap& map, Params& p, int ksteps, i
   if (p.stages < 2) DAV_THROW(DAV_ERR_CUDA, "not enough shared memory for the matvec pipeline");
   p.ws = ws;
   const size_t smem = (size_t)p.stages * STAGE_BYTES + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CK(cudaFuncSetAttribute(matvec_kernel<NT, WARPS_N, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 256));
-    attr_set = true;
-  }
+  ensure_dyn_smem(matvec_kernel<NT, WARPS_N, BK>, max_smem - 256);  // per (kernel, device)
   matvec_kernel<NT, WARPS_N, BK><<<grid, THREADS, smem, s>>>(map, p);
   CK_LAUNCH();
   ++g_kernel_launches;
@@ -648,6 +644,52 @@ MatvecPlan* matvec_plan_create(const double* A, int64_t M, int64_t K, int64_t ld
 
 void matvec_plan_destroy(MatvecPlan* p) { delete p; }
 
+// one chunk of bc <= 128 columns whose packed X block (Kpad x bpad, fragment order) is at Xp
+static void launch_chunk(cudaStream_t s, MatvecPlan* plan, int BK, int64_t Kpad, int bc, const double* Xp, double* W,
+                         int64_t ldw) {
+  int warps_n, nt, bpad;
+  pick_cfg(bc, &warps_n, &nt, &bpad);
+  Params p;
+  p.M = plan->M; p.K = plan->K; p.b = bc;
+  const int ksteps = (int)(Kpad / BK);
+  p.Xp = Xp;
+  p.W = W;
+  p.ldw = ldw;
+  {
+    static const int hints = [] { const char* e = std::getenv("DAV_MATVEC_L2_HINTS"); return e ? std::atoi(e) : 2; }();
+    p.l2_hints = hints;
+  }
+  const int schedule = schedule_for(bpad);
+#define CFG(NT_, WN_)                                                                                          \
+  do {                                                                                                         \
+    if (BK == 32)                                                                                              \
+      launch_cfg<NT_, WN_, 32>(s, plan->map32, p, ksteps, plan->max_smem, plan->num_sms, plan->ws.p, plan->ws.n, \
+                               schedule);                                                                      \
+    else                                                                                                       \
+      launch_cfg<NT_, WN_, 16>(s, plan->map, p, ksteps, plan->max_smem, plan->num_sms, plan->ws.p, plan->ws.n,   \
+                               schedule);                                                                      \
+  } while (0)
+  if (warps_n == 1) {
+    switch (nt) {
+      case 1: CFG(1, 1); break;
+      case 2: CFG(2, 1); break;
+      case 3: CFG(3, 1); break;
+      default: CFG(4, 1); break;
+    }
+  } else if (warps_n == 2) {
+    switch (nt) {
+      case 3: CFG(3, 2); break;
+      default: CFG(4, 2); break;
+    }
+  } else {
+    switch (nt) {
+      case 3: CFG(3, 4); break;
+      default: CFG(4, 4); break;
+    }
+  }
+#undef CFG
+}
+
 void matvec_dmma(cudaStream_t s, MatvecPlan* plan, int b, const double* X, int64_t ldx, double* W, int64_t ldw) {
   if (b <= 0 || plan->M <= 0) return;
   const int BK = bk_from_env();
@@ -664,46 +706,29 @@ void matvec_dmma(cudaStream_t s, MatvecPlan* plan, int b, const double* X, int64
       CK_LAUNCH();
       ++g_kernel_launches;
     }
-    Params p;
-    p.M = plan->M; p.K = plan->K; p.b = bc;
-    const int ksteps = (int)(Kpad / BK);
-    p.Xp = plan->Xp.p;
-    p.W = W + (int64_t)j0 * ldw;
-    p.ldw = ldw;
-    {
-      static const int hints = [] { const char* e = std::getenv("DAV_MATVEC_L2_HINTS"); return e ? std::atoi(e) : 2; }();
-      p.l2_hints = hints;
-    }
-    const int schedule = schedule_for(bpad);
-#define CFG(NT_, WN_)                                                                                          \
-  do {                                                                                                         \
-    if (BK == 32)                                                                                              \
-      launch_cfg<NT_, WN_, 32>(s, plan->map32, p, ksteps, plan->max_smem, plan->num_sms, plan->ws.p, plan->ws.n, \
-                               schedule);                                                                      \
-    else                                                                                                       \
-      launch_cfg<NT_, WN_, 16>(s, plan->map, p, ksteps, plan->max_smem, plan->num_sms, plan->ws.p, plan->ws.n,   \
-                               schedule);                                                                      \
-  } while (0)
-    if (warps_n == 1) {
-      switch (nt) {
-        case 1: CFG(1, 1); break;
-        case 2: CFG(2, 1); break;
-        case 3: CFG(3, 1); break;
-        default: CFG(4, 1); break;
-      }
-    } else if (warps_n == 2) {
-      switch (nt) {
-        case 3: CFG(3, 2); break;
-        default: CFG(4, 2); break;
-      }
-    } else {
-      switch (nt) {
-        case 3: CFG(3, 4); break;
-        default: CFG(4, 4); break;
-      }
-    }
-#undef CFG
+    launch_chunk(s, plan, BK, Kpad, bc, plan->Xp.p, W + (int64_t)j0 * ldw, ldw);
   }
+}
+
+int64_t matvec_kpad(int64_t K) { return round_up(K, bk_from_env()); }
+
+size_t matvec_packed_doubles(int64_t K, int b) {
+  if (b <= 0) return 0;
+  const int nchunks = (b + 127) / 128;
+  int warps_n, nt, bpad;
+  pick_cfg(b - (nchunks - 1) * 128, &warps_n, &nt, &bpad);
+  return ((size_t)(nchunks - 1) * 128 + (size_t)bpad) * (size_t)matvec_kpad(K);
+}
+
+// X already packed (by Comm::gather_rows_packed: every rank stored its rows into this rank's copy): chunk c of 128
+// columns starts at c * 128 * Kpad
+void matvec_dmma_packed(cudaStream_t s, MatvecPlan* plan, int b, const double* Xpacked, double* W, int64_t ldw) {
+  if (b <= 0 || plan->M <= 0) return;
+  const int BK = bk_from_env();
+  const int64_t Kpad = round_up(plan->K, BK);
+  for (int j0 = 0; j0 < b; j0 += 128)
+    launch_chunk(s, plan, BK, Kpad, std::min(128, b - j0), Xpacked + (size_t)j0 * (size_t)Kpad, W + (int64_t)j0 * ldw,
+                 ldw);
 }
 
 }  // namespace dav

@@ -501,12 +501,13 @@ __global__ void __launch_bounds__(1024) cholesky_upper_kernel(int k, double* G, 
 // ((i,j), i <= j, at i + j(j+1)/2).  T <- R^-1 (dense b x b, zero below the diagonal).  flag[0] = 1.0 when a
 // pivot is not safely positive (the caller then falls back to the SVQB transform), else 0.0.  G is only read.
 __global__ void __launch_bounds__(512) chol_inv_upper_kernel(int b, const double* __restrict__ G, double* __restrict__ T,
-                                                             double* __restrict__ flag) {
+                                                             double* __restrict__ flag, double* gwork) {
   extern __shared__ __align__(16) double sm[];
   const int tri = b * (b + 1) / 2;
-  double* R = sm;
-  double* X = sm + tri;
-  double* d0 = X + tri;
+  // gwork != nullptr: the triangles do not fit in shared memory (b >= ~170) and live in global scratch
+  double* R = gwork ? gwork : sm;
+  double* X = R + tri;
+  double* d0 = gwork ? sm : X + tri;
   __shared__ int bad;
   const int tid = threadIdx.x, nt = blockDim.x;
   if (tid == 0) bad = 0;
@@ -653,15 +654,10 @@ void jacobi_eigh(cudaStream_t s, int k, double* S, double* Y, double* w, double*
                  const int* skip) {
   if (k <= 0) return;
   const int kp = k + (k & 1), np = kp / 2;
-  static int max_smem = -1;
-  if (max_smem < 0) {
-    int dev = 0;
-    CK(cudaGetDevice(&dev));
-    CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    CK(cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    CK(cudaFuncSetAttribute(jacobi_sweeps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    CK(cudaFuncSetAttribute(jacobi_vectors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  }
+  const int max_smem = device_max_smem_optin();
+  ensure_dyn_smem(jacobi_kernel, max_smem);
+  ensure_dyn_smem(jacobi_sweeps_kernel, max_smem);
+  ensure_dyn_smem(jacobi_vectors_kernel, max_smem);
   // ---- fast path: S in shared memory, rotations logged, V replayed by a second kernel
   {
     const int nitems = np * (np + 1) / 2;
@@ -738,18 +734,20 @@ void cholesky_upper(cudaStream_t s, int k, double* G, int64_t ld, int* status) {
   ++g_kernel_launches;
 }
 
-bool chol_inv_upper(cudaStream_t s, int b, const double* G, double* T, double* flag) {
-  static int max_smem = -1;
-  if (max_smem < 0) {
-    int dev = 0;
-    CK(cudaGetDevice(&dev));
-    CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    CK(cudaFuncSetAttribute(chol_inv_upper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 1024));
-  }
-  const size_t bytes = ((size_t)b * (b + 1) + b) * sizeof(double);
-  if (bytes > (size_t)max_smem - 1024) return false;
+bool chol_inv_upper(cudaStream_t s, int b, const double* G, double* T, double* flag, double* gwork,
+                    size_t gwork_doubles) {
+  const int max_smem = device_max_smem_optin();
+  ensure_dyn_smem(chol_inv_upper_kernel, max_smem - 1024);
+  const size_t tri2 = (size_t)b * (b + 1);
+  const size_t bytes = (tri2 + b) * sizeof(double);
   const int threads = b <= 32 ? 128 : (b <= 64 ? 256 : 512);
-  chol_inv_upper_kernel<<<1, threads, bytes, s>>>(b, G, T, flag);
+  if (bytes <= (size_t)max_smem - 1024) {
+    chol_inv_upper_kernel<<<1, threads, bytes, s>>>(b, G, T, flag, nullptr);
+  } else {
+    // wide blocks (b >= ~170): both triangles live in L2-resident global scratch, only the diagonal in shared memory
+    if (!gwork || gwork_doubles < tri2) return false;
+    chol_inv_upper_kernel<<<1, 512, (size_t)b * sizeof(double), s>>>(b, G, T, flag, gwork);
+  }
   CK_LAUNCH();
   ++g_kernel_launches;
   return true;

@@ -57,6 +57,8 @@ dav_solver::dav_solver(int device_, int rank, int world, const void* id128) : de
 
 dav_solver::~dav_solver() {
   cudaSetDevice(device);
+  comm.sym_release(xsym);
+  comm.sym_release(xpk);
   for (int w = 0; w < 2; ++w) {
     if (mat[w].plan) matvec_plan_destroy(mat[w].plan);
     if (mat[w].ftab) free_tables_destroy(mat[w].ftab);
@@ -302,6 +304,16 @@ const double* dav_solver::gather_rows(const double* Xlocal, int64_t ldx, int b, 
     *ld_out = ldx;
     return Xlocal;
   }
+  if (comm.peer()) {
+    // every rank stores its rows straight into every peer's copy of the block: one kernel, no staging passes
+    comm.sym_reserve(xsym, (size_t)n * b * 8, stream);  // no-op inside a solve (reserved by alloc_work)
+    const int sp = begin_span(SPAN_COMM);
+    comm.gather_rows(Xlocal, ldx, nl, row0, n, b, xsym, stream);
+    end_span(sp);
+    stats.collectives += 1;
+    *ld_out = n;
+    return xsym.p();
+  }
   stage_s.alloc((size_t)chunk * b);
   stage_r.alloc((size_t)chunk * b * comm.world());
   Xfull.alloc((size_t)n * b);
@@ -359,10 +371,30 @@ void dav_solver::apply_full(int which, const double* Xf, int64_t ldx, int b, dou
     DAV_THROW(DAV_ERR_STATE, "no matrix set in slot %d", which);
   }
   end_span(sp);
+  count_matvec(b);
+}
+
+void dav_solver::count_matvec(int b) {
   stats.matvec_launches += 1;
   stats.matvec_bytes += 8.0 * (double)nl * (double)n + 8.0 * (double)n * b + 8.0 * (double)nl * b;
   stats.matvec_flops += 2.0 * (double)nl * (double)n * b;
   stats.last_matvec_b = b;
+}
+
+// NB: every term is identical on all ranks (the ranks must take the same branch around a collective)
+bool dav_solver::packed_gather_usable() const {
+  if (!comm.peer() || matvec_impl == DAV_MATVEC_SIMT || !matvec_dmma_supported()) return false;
+  if ((int64_t)(comm.world() - 1) * chunk >= n) return false;  // some rank owns no rows (and has no plan)
+  for (int w = 0; w < 2; ++w)
+    if (mat[w].kind != NONE && mat[w].kind != DENSE) return false;
+  return true;
+}
+
+void dav_solver::apply_packed(int which, int b, double* W, int64_t ldw) {
+  const int sp = begin_span(SPAN_MATVEC);
+  matvec_dmma_packed(stream, mat[which].plan, b, xpk.p(), W, ldw);
+  end_span(sp);
+  count_matvec(b);
 }
 
 void dav_solver::alloc_work(int lowest, int kcap_) {
@@ -382,8 +414,8 @@ void dav_solver::alloc_work(int lowest, int kcap_) {
   status.alloc(4);
   flags.alloc(kcap);
   idx.alloc(2 * (size_t)lowest);
-  cand_val.alloc((size_t)2 * lowest * std::max(1, comm.world()) + 2 * (size_t)lowest);
-  cand_idx.alloc((size_t)2 * lowest * std::max(1, comm.world()) + 2 * (size_t)lowest);
+  // [values | indices] of this rank's 2L candidates, then [all values | all indices] of every rank
+  cand_val.alloc((size_t)4 * lowest * (std::max(1, comm.world()) + 1));
   {
     const size_t e = std::max(topk_scratch_entries(nl, 2 * lowest),
                               topk_scratch_entries((int64_t)2 * lowest * std::max(1, comm.world()), 2 * lowest));
@@ -393,12 +425,18 @@ void dav_solver::alloc_work(int lowest, int kcap_) {
   // everything the loop touches is allocated up front: no cudaMalloc inside the iteration
   const int bmax = std::max(2 * lowest, kcap / 2);
   const bool any_free = mat[0].kind != DENSE || (mat[1].kind != NONE && mat[1].kind != DENSE);
-  if (comm.active() || any_free) Xfull.alloc((size_t)n * bmax);
-  if (comm.active()) {
-    stage_s.alloc((size_t)chunk * bmax);
-    stage_r.alloc((size_t)chunk * bmax * comm.world());
-  }
   for (int w = 0; w < 2; ++w) ensure_plan(w, bmax);
+  if (comm.active()) comm.reserve_allreduce(kk, stream);  // collective; decides the transport on the first call
+  if (comm.peer()) {
+    comm.sym_reserve(xsym, (size_t)n * bmax * 8, stream);
+    if (packed_gather_usable()) comm.sym_reserve(xpk, matvec_packed_doubles(n, bmax) * 8, stream);
+  } else {
+    if (comm.active() || any_free) Xfull.alloc((size_t)n * bmax);
+    if (comm.active()) {
+      stage_s.alloc((size_t)chunk * bmax);
+      stage_r.alloc((size_t)chunk * bmax * comm.world());
+    }
+  }
 }
 
 void dav_solver::check_status(const char* where) {
@@ -476,7 +514,8 @@ void dav_solver::orthonormalize_block(double* Cblk, int b, int kold, double* des
     allreduce(S1.p, (size_t)b * b);
     max_abs_dev(stream, kold, b, G.p, kold, false, small.p);
     max_abs_dev(stream, b, b, S1.p, b, true, small.p + 1);
-    const bool tried_chol = chol_inv_upper(stream, b, S1.p, Tm.p, small.p + 2);
+    // wide blocks (b >= ~170) factorise in global scratch: Z (kcap^2 doubles >= b (b+1)) is free in this routine
+    const bool tried_chol = chol_inv_upper(stream, b, S1.p, Tm.p, small.p + 2, Z.p, Z.n);
     double h[3] = {0.0, 0.0, 1.0};
     CK(cudaMemcpyAsync(h, small.p, (tried_chol ? 3 : 2) * sizeof(double), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
@@ -509,19 +548,13 @@ void dav_solver::orthonormalize_block(double* Cblk, int b, int kold, double* des
 bool dav_solver::orthonormalize_block_pip(int b, int kold) {
   const int kb = kold + b;
   if (kb > kcap || (size_t)kb * b > G.n) return false;
-  {
-    // chol_inv_upper needs the b x b triangle pair in shared memory
-    int dev = 0, max_smem = 0;
-    CK(cudaGetDevice(&dev));
-    CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    if (((size_t)b * (b + 1) + b) * sizeof(double) > (size_t)max_smem - 1024) return false;
-  }
+  if ((size_t)b * (b + 1) > jscratch.n) return false;  // global scratch of the wide-block Cholesky
   const int sp = begin_span(SPAN_ORTH);
   double* Vnew = V.p + (size_t)kold * ldv;
   auto small_ops = [&](int pass) {  // G.p = Gall (kb x b) -> Z.p = M (kb x b); metrics in small.p[4*pass ..]
     gemm(stream, true, b, b, kold, 1.0, G.p, kb, G.p, kb, 0.0, S1.p, b, nullptr, 0);  // P = H^T H
     pip_prepare(stream, kold, b, G.p, S1.p, S2.p, D.p, small.p + 4 * pass);
-    chol_inv_upper(stream, b, S2.p, U.p, small.p + 4 * pass + 3);
+    chol_inv_upper(stream, b, S2.p, U.p, small.p + 4 * pass + 3, jscratch.p, jscratch.n);
     pip_finish(stream, kold, b, U.p, D.p, Tm.p, Z.p);
     gemm(stream, false, kold, b, b, -1.0, G.p, kb, Tm.p, b, 0.0, Z.p, kb, nullptr, 0);  // rows 0..k: -H Tm
   };
@@ -588,17 +621,20 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
   int sp = begin_span(SPAN_INIT);
   ensure_diag(0);
   if (gev) ensure_diag(1);
-  topk_smallest(stream, mat[0].diag.p, nullptr, nl, row0, k0, cand_val.p, cand_idx.p, status.p, topk_val.p,
-                topk_idx.p);
+  double* cv = cand_val.p;
+  int64_t* ci = reinterpret_cast<int64_t*>(cand_val.p + k0);
+  topk_smallest(stream, mat[0].diag.p, nullptr, nl, row0, k0, cv, ci, status.p, topk_val.p, topk_idx.p);
   if (comm.active()) {
     const int P = comm.world();
-    double* allv = cand_val.p + k0;
-    int64_t* alli = cand_idx.p + k0;
-    allgather(cand_val.p, allv, (size_t)k0 * 8);
-    allgather(cand_idx.p, alli, (size_t)k0 * 8);
-    topk_smallest(stream, allv, alli, (int64_t)k0 * P, 0, k0, cand_val.p, idx.p, status.p, topk_val.p, topk_idx.p);
+    double* allv = cand_val.p + 2 * k0;
+    int64_t* alli = reinterpret_cast<int64_t*>(allv + (size_t)k0 * P);
+    const int spc = begin_span(SPAN_COMM);
+    comm.allgather2(cv, allv, (size_t)k0 * 8, (size_t)k0 * 8, stream);  // values and indices in one exchange
+    end_span(spc);
+    stats.collectives += 1;
+    topk_smallest(stream, allv, alli, (int64_t)k0 * P, 0, k0, cv, idx.p, status.p, topk_val.p, topk_idx.p);
   } else {
-    CK(cudaMemcpyAsync(idx.p, cand_idx.p, (size_t)k0 * 8, cudaMemcpyDeviceToDevice, stream));
+    CK(cudaMemcpyAsync(idx.p, ci, (size_t)k0 * 8, cudaMemcpyDeviceToDevice, stream));
   }
   int k = k0;
   fill_zero(stream, V.p, (size_t)ldv * k);
@@ -711,13 +747,21 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
       copy_matrix(stream, nl, k, C.p, ldv, Q, ldv);                   // [V | C] contiguous
       if (!orthonormalize_block_pip(k, k))                            // steps 6-7 (:210-213)
         orthonormalize_block(Q, k, k, Q);
+      const bool packed = packed_gather_usable() && xpk.bytes >= matvec_packed_doubles(n, k) * 8;
       int64_t ldf = 0;
+      const double* Qf = nullptr;
       const int spg = begin_span(SPAN_GATHER);
-      const double* Qf = gather_rows(Q, ldv, k, &ldf);                // one all-gather for both matrices
+      if (packed) {  // every rank stores its rows of Q straight into every peer's packed operand of the matvec
+        comm.gather_rows_packed(Q, ldv, nl, row0, n, matvec_kpad(n), k, xpk, stream);
+        stats.collectives += 1;
+      } else {
+        Qf = gather_rows(Q, ldv, k, &ldf);                            // one all-gather for both matrices
+      }
       end_span(spg);
       for (int w = 0; w < (gev ? 2 : 1); ++w) {
         double* W = (w ? BV.p : AV.p) + (size_t)k * ldv;
-        apply_full(w, Qf, ldf, k, W, ldv);                            // the block matvec
+        if (packed) apply_packed(w, k, W, ldv);                       // the block matvec
+        else apply_full(w, Qf, ldf, k, W, ldv);
         project_new_block(w, k, k);
       }
       k *= 2;

@@ -37,10 +37,13 @@ struct dav_solver {
   int64_t ldv = 0;
   int kcap = 0;
   dav::DevBuf<double> V, AV, BV, R, C, T, Xfull, stage_s, stage_r;
+  // peer transport (comm.cuh): every rank's copy of the gathered block, written by all ranks directly
+  dav::SymBuf xsym;  // n x b column-major (generic consumers: matrix-free operators, output, SIMT kernels)
+  dav::SymBuf xpk;   // packed MMA-fragment order (the dense TMA/DMMA matvec)
   dav::DevBuf<double> Ap, Bp, Y, theta, G, U, sv, D, Tm, S1, S2, Z, jscratch, norms2, partial, gemm_ws, small;
   dav::DevBuf<int> status, flags, gjd_active;
   dav::DevBuf<double> gjd_buf, gjd_st;
-  dav::DevBuf<int64_t> idx, cand_idx, topk_idx;
+  dav::DevBuf<int64_t> idx, topk_idx;
   dav::DevBuf<double> cand_val, topk_val;
   std::vector<double> host_x, host_y;  // callback staging
   // page-locked staging of the eigenvectors on their way to the caller's (pageable) array: a direct device ->
@@ -74,6 +77,11 @@ struct dav_solver {
   // same with X already complete (n x b) on this rank
   void apply_full(int which, const double* Xfull_, int64_t ldx, int b, double* W, int64_t ldw);
   const double* gather_rows(const double* Xlocal, int64_t ldx, int b, int64_t* ld_out);
+  // true when the new block can go straight into every peer's packed copy (all matrices dense on the DMMA path)
+  bool packed_gather_usable() const;
+  // W = M_which * X for the block last gathered with comm.gather_rows_packed into xpk
+  void apply_packed(int which, int b, double* W, int64_t ldw);
+  void count_matvec(int b);
 
   int solve(int lowest, int method, int max_iterations, double tolerance, int max_dim_sub, double* eigenvalues,
             double* eigenvectors, int64_t ldvec, int* iters);

@@ -562,19 +562,14 @@ void sym_eigh(cudaStream_t s, int k, double* S, double* Y, double* w, double* sc
     jacobi_eigh(s, k, S, Y, w, scratch, status, nullptr);
     return;
   }
-  static int max_smem = -1;
-  if (max_smem < 0) {
-    int dev = 0;
-    CK(cudaGetDevice(&dev));
-    CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    CK(cudaFuncSetAttribute(tridiag_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 2048));
-    CK(cudaFuncSetAttribute(tridiag_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 2048));
-    CK(cudaFuncSetAttribute(tridiag_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 2048));
-    CK(cudaFuncSetAttribute(tri_eigvec_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    CK(cudaFuncSetAttribute(tri_eigvec_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    CK(cudaFuncSetAttribute(tri_eigvec_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    CK(cudaFuncSetAttribute(tri_eigvec_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  }
+  const int max_smem = device_max_smem_optin();
+  ensure_dyn_smem(tridiag_kernel<2>, max_smem - 2048);  // per (kernel, device)
+  ensure_dyn_smem(tridiag_kernel<5>, max_smem - 2048);
+  ensure_dyn_smem(tridiag_kernel<8>, max_smem - 2048);
+  ensure_dyn_smem(tri_eigvec_kernel<2>, max_smem);
+  ensure_dyn_smem(tri_eigvec_kernel<4>, max_smem);
+  ensure_dyn_smem(tri_eigvec_kernel<8>, max_smem);
+  ensure_dyn_smem(tri_eigvec_kernel<16>, max_smem);
   const size_t kk = (size_t)k * k;
   double* base = scratch + jacobi_scratch_doubles(k);
   double* work = base;            // tridiagonalisation workspace when S does not fit in shared memory

@@ -1,12 +1,54 @@
 // n x k vector-block kernels, generators and layout helpers.  All HBM-bound streaming kernels:
 // coalesced along the row index (column-major blocks), grids sized in multiples of the SM count.
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "kernels.cuh"
 
 namespace dav {
+
+// ---- per-device facts / one-time kernel settings (common.cuh) ---------------------------------------------------
+namespace {
+constexpr int MAX_DEVICES = 64;
+struct DevFacts { int max_smem = -1, sms = -1; };
+std::mutex g_dev_mu;
+DevFacts g_dev[MAX_DEVICES];
+std::map<std::pair<const void*, int>, int> g_smem_set;  // (kernel, device) -> bytes already granted
+
+const DevFacts& dev_facts() {
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= MAX_DEVICES) DAV_THROW(DAV_ERR_CUDA, "device ordinal %d out of range", dev);
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  DevFacts& f = g_dev[dev];
+  if (f.max_smem < 0) {
+    CK(cudaDeviceGetAttribute(&f.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    CK(cudaDeviceGetAttribute(&f.sms, cudaDevAttrMultiProcessorCount, dev));
+    if (f.sms <= 0) f.sms = 148;
+  }
+  return f;
+}
+}  // namespace
+
+int device_max_smem_optin() { return dev_facts().max_smem; }
+int device_num_sms() { return dev_facts().sms; }
+
+void ensure_dyn_smem_impl(const void* func, int bytes) {
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  int& have = g_smem_set[std::make_pair(func, dev)];
+  if (have >= bytes) return;
+  CK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  have = bytes;
+}
+
 namespace {
 
+// grid sizing: a few CTAs per SM of the B200 (148 SMs); a different SM count only changes the number of grid-stride
+// iterations, never the result
 constexpr int SMS = 148;
 
 __global__ void fill_zero_kernel(double* p, size_t count) {

@@ -239,6 +239,18 @@ class DavidsonSolver:
         check(lib().dav_bench_fp64_pipe(self._h, C.c_int(reps), C.byref(out)))
         return out.value
 
+    def debug_collective(self, kind, count, reps=20):
+        """(microseconds per call, max abs error) of one inter-GPU exchange; see dav_debug_collective."""
+        out = (C.c_double * 2)()
+        check(lib().dav_debug_collective(self._h, C.c_int(kind), C.c_int64(count), C.c_int(reps), out))
+        return out[0], out[1]
+
+    def comm_info(self):
+        """{'peer': bool, 'peer_calls': int, 'nccl_calls': int} of a distributed handle."""
+        p, a, b = C.c_int(0), C.c_longlong(0), C.c_longlong(0)
+        check(lib().dav_comm_info(self._h, C.byref(p), C.byref(a), C.byref(b)))
+        return {"peer": bool(p.value), "peer_calls": a.value, "nccl_calls": b.value}
+
     def bench_block_matvec(self, which, b, reps):
         ms = (C.c_float * reps)()
         check(lib().dav_bench_block_matvec(self._h, C.c_int(which), C.c_int64(b), C.c_int(reps), ms))

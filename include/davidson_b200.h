@@ -193,6 +193,18 @@ int dav_bench_fp64_pipe(dav_solver_t* h, int reps, double* dmma_tflops);
  * multi-GPU tile shapes. */
 int dav_debug_matvec_rect(int device, int64_t m, int64_t k, int b, double* max_abs_diff, double* scale);
 
+/* Self-check and timing of the inter-GPU exchanges of a distributed handle (collective: every rank calls it with the
+ * same arguments).  kind 0 = all-reduce on the transport in use (peer-memory kernel when the GPUs map each other,
+ * else NCCL), 1 = all-reduce through NCCL, 2 = gather of an n x count block (every rank stores its rows into every
+ * peer's copy), 3 = the same into the packed MMA-fragment order of the block matvec.  count = doubles (kinds 0, 1)
+ * or columns (2, 3; a matrix must be set: the handle's row partition is used).
+ * out2[0] = microseconds per call (CUDA events over `reps` back-to-back calls), out2[1] = max abs error against the
+ * analytically known result. */
+int dav_debug_collective(dav_solver_t* h, int kind, int64_t count, int reps, double* out2);
+/* transport of a distributed handle: *peer_transport = 1 when the exchanges are the library's own peer-memory
+ * kernels (0: NCCL); calls issued so far on either transport. */
+int dav_comm_info(dav_solver_t* h, int* peer_transport, long long* peer_calls, long long* nccl_calls);
+
 /* Host-only check of the block-matvec work schedule (full waves + stream-K remainder) for an M x K local block and
  * a b-column block on a device with num_sms SMs: runs the very functions the kernel and its fixup pass use and
  * verifies that every (row tile, k step) unit is computed exactly once and every partial tile is summed exactly

@@ -57,6 +57,7 @@ def main():
     assert abs(iters - r.iters) <= 1 and np.abs(ev - r.eigenvalues).max() / np.abs(ev).max() < 1e-10
     if rank == 0:
         print("ok free benchmark n=1000 iters=%d" % iters)
+        print("comm", s.comm_info())
         print("DIST_GPU_CHECK_PASSED world=%d" % world)
     s.close()
 
