@@ -378,6 +378,32 @@ int dav_debug_collective(dav_solver_t* h, int kind, int64_t count, int reps, dou
   API_END
 }
 
+int dav_debug_chol_inv(int b, const double* g, double* t, double* flag, float* ms) {
+  API_BEGIN
+  need(b >= 1 && g && t && flag, "bad arguments");
+  Ctx c;
+  DevBuf<double> G, T, F, W;
+  const size_t bb = (size_t)b * b;
+  G.alloc(bb); T.alloc(bb); F.alloc(1); W.alloc(bb + b);
+  h2d(G.p, g, bb, c.s);
+  need(chol_inv_upper(c.s, b, G.p, T.p, F.p, W.p, W.n), "chol_inv_upper: no kernel for this width");  // warm-up
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, c.s));
+  chol_inv_upper(c.s, b, G.p, T.p, F.p, W.p, W.n);
+  CK(cudaEventRecord(e1, c.s));
+  d2h(t, T.p, bb, c.s);
+  d2h(flag, F.p, 1, c.s);
+  c.sync();
+  float dt = 0.f;
+  CK(cudaEventElapsedTime(&dt, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (ms) *ms = dt;
+  API_END
+}
+
 int dav_comm_info(dav_solver_t* h, int* peer_transport, long long* peer_calls, long long* nccl_calls) {
   API_BEGIN
   need(h, "bad handle");

@@ -108,44 +108,96 @@ __device__ __forceinline__ bool last_cta_arrives(unsigned int* counter) {
   return is_last != 0;
 }
 
-// One-shot all-reduce.  slot layout on every rank: [parity][source rank][cap].  Two parities: a rank can start
-// all-reduce e+1 (storing into parity (e+1)&1) while a slower peer still adds the slots of e, but not e+2 -- that
-// needs the peer's flag for e+1, which the peer raises only after it has finished reading e (stream order).
-// gather_out != nullptr: no sum, a small all-gather of two segments: words [0, seg) of rank p go to
-// gather_out[p * seg + i], words [seg, count) behind all first segments (seg == count: plain all-gather).
-__global__ void __launch_bounds__(256) peer_allreduce_kernel(PeerArgs a, double* __restrict__ buf, size_t count,
-                                                             size_t cap, unsigned long long epoch,
-                                                             double* __restrict__ gather_out, size_t seg) {
-  const int P = a.world, r = a.rank;
-  const size_t par = (size_t)(epoch & 1ULL) * (size_t)P * cap;
-  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gs = (size_t)gridDim.x * blockDim.x;
-  PeerCtl* me = a.ctl[r];
-  for (size_t i = gt; i < count; i += gs) {
-    const double v = buf[i];
-#pragma unroll 4
-    for (int p = 0; p < P; ++p) a.data[p][par + (size_t)r * cap + i] = v;
-  }
-  if (last_cta_arrives(&me->counter[0])) {
-    if ((int)threadIdx.x < P) {
-      __threadfence_system();
-      st_release_sys(&a.ctl[threadIdx.x]->ar_flag[r], epoch);
+// ---- low-latency one-shot reduction (the small exchanges: projection / Gram partials, norms, candidates) -------
+// Every 8-byte word travels in a 16-byte line {lo32, flag, hi32, flag} written with ONE 16-byte store; the receiver
+// polls the line itself until both flags carry this call's number -- no fence, no separate flag, no counter: one
+// NVLink one-way latency per exchange (the LL protocol of NCCL, which relies only on 8-byte store atomicity).
+// Line layout on every rank: [parity][source rank][cap].  Two parities: a rank can start exchange e+1 (parity
+// (e+1)&1) while a slower peer still polls the lines of e, but not e+2 -- that needs the peer's lines of e+1, which
+// the peer stores only after its kernel of e has finished (stream order).  Flags never repeat within a parity
+// (the call number itself, 32 bit), lines start zeroed, call numbers start at 1.
+struct LLArgs {
+  uint4* ll[COMM_MAX_RANKS];
+  int rank, world;
+};
+
+__device__ __forceinline__ void ll_store(uint4* p, double v, unsigned flag) {
+  const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)u), "r"(flag),
+               "r"((unsigned)(u >> 32)), "r"(flag)
+               : "memory");
+}
+__device__ __forceinline__ double ll_wait(const uint4* p, unsigned flag, int* error) {
+  unsigned lo, f1, hi, f2;
+  unsigned spins = 0;
+  unsigned long long t0 = 0;
+  for (;;) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f1), "=r"(hi), "=r"(f2) : "l"(p)
+                 : "memory");
+    if (f1 == flag && f2 == flag) break;
+    if ((++spins & 4095u) == 0) {  // a peer died: end with an error instead of hanging the GPU
+      if (t0 == 0) t0 = globaltimer_ns();
+      else if (globaltimer_ns() - t0 > 4000000000ULL) { *error = 1; break; }
     }
   }
-  if ((int)threadIdx.x < P) wait_flag(&me->ar_flag[threadIdx.x], epoch, &me->error);
-  __syncthreads();
-  const double* mine = a.data[r] + par;
-  if (gather_out) {
-    for (size_t i = gt; i < count; i += gs)
-      for (int p = 0; p < P; ++p) {
-        const size_t o = i < seg ? (size_t)p * seg + i : (size_t)P * seg + (size_t)p * (count - seg) + (i - seg);
-        gather_out[o] = __ldcg(mine + (size_t)p * cap + i);
-      }
-    return;
+  return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+}
+
+// out modes of the reduction (ReduceOut in comm.cuh)
+__device__ __forceinline__ void reduce_store(const ReduceOut& o, int64_t M, int64_t e, double v) {
+  const int64_t m = e % M, j = e / M;
+  if (o.mode == 0) {
+    o.C[m + j * o.ldc] = v;
+  } else if (o.mode == 1) {
+    // block column kold.. of a projected matrix: the upper part is stored, the strictly upper part mirrored
+    const int64_t c = o.kold + j;
+    if (m <= c) o.C[m + c * o.ldc] = v;
+    if (m < c) o.C[c + m * o.ldc] = v;
+  } else {
+    // two-segment gather (no sum is formed by the caller in this mode): handled in the kernel
   }
-  for (size_t i = gt; i < count; i += gs) {
-    double s = 0.0;
-    for (int p = 0; p < P; ++p) s += __ldcg(mine + (size_t)p * cap + i);  // rank order: identical on every rank
-    buf[i] = s;
+}
+
+// value e = sum over z of src[z * total + e] (split-K partials, fixed order), summed over the ranks in rank order
+// (bit-identical on every rank), stored according to `out`.  world == 1: no exchange.
+// gather_seg >= 0: no rank sum; out.C[...] receives every rank's words (two-segment all-gather, see allgather2).
+__global__ void __launch_bounds__(256) ll_reduce_kernel(LLArgs a, const double* __restrict__ src, int splits,
+                                                        int64_t M, int64_t total, size_t cap, unsigned flag, int par,
+                                                        ReduceOut out, int64_t gather_seg, int* error) {
+  const int P = a.world, r = a.rank;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int z = 0;
+    for (; z + 3 < splits; z += 4) {
+      s0 += src[(size_t)z * total + e];
+      s1 += src[(size_t)(z + 1) * total + e];
+      s2 += src[(size_t)(z + 2) * total + e];
+      s3 += src[(size_t)(z + 3) * total + e];
+    }
+    if (z < splits) s0 += src[(size_t)z * total + e];
+    if (z + 1 < splits) s1 += src[(size_t)(z + 1) * total + e];
+    if (z + 2 < splits) s2 += src[(size_t)(z + 2) * total + e];
+    double v = ((s0 + s1) + s2) + s3;
+    if (P > 1) {
+      const size_t line = ((size_t)par * P + r) * cap + (size_t)e;
+#pragma unroll 4
+      for (int q = 1; q < P; ++q) ll_store(a.ll[(r + q) % P] + line, v, flag);  // peers staggered
+      const uint4* mine = a.ll[r] + (size_t)par * P * cap + (size_t)e;
+      if (gather_seg >= 0) {
+        const int64_t count = total;
+        for (int p = 0; p < P; ++p) {
+          const double w = (p == r) ? v : ll_wait(mine + (size_t)p * cap, flag, error);
+          const int64_t o = e < gather_seg ? (int64_t)p * gather_seg + e
+                                           : (int64_t)P * gather_seg + (int64_t)p * (count - gather_seg) + (e - gather_seg);
+          out.C[o] = w;
+        }
+        continue;
+      }
+      double t = 0.0;
+      for (int p = 0; p < P; ++p) t += (p == r) ? v : ll_wait(mine + (size_t)p * cap, flag, error);
+      v = t;
+    }
+    reduce_store(out, M, e, v);
   }
 }
 
@@ -486,7 +538,7 @@ void Comm::reserve_allreduce(size_t max_count, cudaStream_t s) {
   if (!peer_) return;
   if (max_count <= slot_cap_) return;
   const size_t cap = (size_t)round_up((int64_t)max_count, 32);
-  sym_reserve(slots_, 2 * (size_t)world_ * cap * sizeof(double), s);
+  sym_reserve(slots_, 2 * (size_t)world_ * cap * 16, s);  // 16-byte lines, zeroed: no line carries a live flag
   slot_cap_ = cap;
 }
 
@@ -495,18 +547,60 @@ void Comm::nccl_allreduce(double* buf, size_t count, cudaStream_t s) {
   ++nccl_calls;
 }
 
+void Comm::launch_ll(const double* src, int splits, int64_t M, int64_t total, const ReduceOut& out, int64_t gather_seg,
+                     bool exchange, cudaStream_t s) {
+  LLArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.rank = rank_;
+  a.world = (exchange && peer_) ? world_ : 1;
+  unsigned flag = 0;
+  int par = 0;
+  if (a.world > 1) {
+    for (int r = 0; r < world_; ++r) a.ll[r] = (uint4*)slots_.peer[r];
+    ++ar_epoch_;
+    if ((ar_epoch_ & 0xffffffffULL) == 0) ar_epoch_ += 2;  // flag 0 is the "empty line" pattern; keep the parity
+    flag = (unsigned)(ar_epoch_ & 0xffffffffULL);
+    par = (int)(ar_epoch_ & 1ULL);
+    ++peer_calls;
+  }
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, 256), 1184));
+  ll_reduce_kernel<<<grid, 256, 0, s>>>(a, src, splits, M, total, slot_cap_, flag, par, out, gather_seg,
+                                        a.world > 1 ? &((PeerCtl*)ctl_.local)->error : nullptr);
+  CK_LAUNCH();
+  ++g_kernel_launches;
+}
+
+void Comm::reduce_sum(const double* src, int splits, int64_t M, int64_t N, const ReduceOut& out, cudaStream_t s) {
+  const int64_t total = M * N;
+  if (total <= 0) return;
+  if (world_ > 1 && (!peer_ || (size_t)total > slot_cap_)) {
+    // NCCL transport: local split-K reduction into a contiguous block, ncclAllReduce, then the output layout
+    nccl_tmp_.alloc((size_t)total);
+    ReduceOut flat;
+    flat.mode = 0;
+    flat.C = nccl_tmp_.p;
+    flat.ldc = M;
+    flat.kold = 0;
+    launch_ll(src, splits, M, total, flat, -1, false, s);
+    nccl_allreduce(nccl_tmp_.p, (size_t)total, s);
+    launch_ll(nccl_tmp_.p, 1, M, total, out, -1, false, s);
+    return;
+  }
+  launch_ll(src, splits, M, total, out, -1, true, s);
+}
+
 void Comm::allreduce_sum(double* buf, size_t count, cudaStream_t s) {
   if (world_ <= 1 || count == 0) return;
   if (!peer_ || count > slot_cap_) {
     nccl_allreduce(buf, count, s);
     return;
   }
-  ++ar_epoch_;
-  const int grid = (int)std::max<size_t>(1, std::min<size_t>((count + 511) / 512, 64));
-  peer_allreduce_kernel<<<grid, 256, 0, s>>>(args_for(slots_), buf, count, slot_cap_, ar_epoch_, nullptr, 0);
-  CK_LAUNCH();
-  ++g_kernel_launches;
-  ++peer_calls;
+  ReduceOut out;
+  out.mode = 0;
+  out.C = buf;
+  out.ldc = (int64_t)count;
+  out.kold = 0;
+  launch_ll(buf, 1, (int64_t)count, (int64_t)count, out, -1, true, s);  // in place: a thread reads its word, then writes it
 }
 
 void Comm::allgather(const void* send, void* recv, size_t bytes_per_rank, cudaStream_t s) {
@@ -522,14 +616,12 @@ void Comm::allgather2(const void* send, void* recv, size_t bytes_a, size_t bytes
   if (peer_ && bytes_a % 8 == 0 && bytes_b % 8 == 0 && bytes / 8 <= slot_cap_ && ((uintptr_t)send & 7) == 0 &&
       ((uintptr_t)recv & 7) == 0) {
     // small payloads ride on the one-shot exchange (8-byte words, no arithmetic on them)
-    const size_t count = bytes / 8;
-    ++ar_epoch_;
-    const int grid = (int)std::max<size_t>(1, std::min<size_t>((count + 511) / 512, 64));
-    peer_allreduce_kernel<<<grid, 256, 0, s>>>(args_for(slots_), (double*)send, count, slot_cap_, ar_epoch_,
-                                               (double*)recv, bytes_a / 8);
-    CK_LAUNCH();
-    ++g_kernel_launches;
-    ++peer_calls;
+    ReduceOut out;
+    out.mode = 2;
+    out.C = (double*)recv;
+    out.ldc = 0;
+    out.kold = 0;
+    launch_ll((const double*)send, 1, (int64_t)(bytes / 8), (int64_t)(bytes / 8), out, (int64_t)(bytes_a / 8), true, s);
     return;
   }
   check(api().AllGather(send, recv, bytes_a, NCCL_UINT8, (ncclComm_t)comm_, s), "ncclAllGather");

@@ -5,9 +5,10 @@
 //     segments with cudaIpc, maps its peers' segments, and the exchanges are OUR kernels storing straight into peer
 //     memory ("push"), followed by a flag with release semantics at system scope.
 //       - all-reduce (k x k projection / Gram partials, residual norms: <= a few 100 KB, latency-bound): one kernel,
-//         one-shot: every rank stores its contribution into slot[rank] of every peer, raises flag[rank] there, waits
-//         for the P flags on its own device and adds the P slots in rank order -> the result is bit-identical on
-//         every rank and independent of arrival order.  ~2 NVLink latencies instead of a ~40 us NCCL call.
+//         one-shot, fused with the split-K reduction that produces the partials and with the layout of the result:
+//         every value travels with its flag in one 16-byte store into line[rank] of every peer; the receiver polls
+//         the lines and adds them in rank order -> bit-identical on every rank, independent of arrival order, one
+//         NVLink latency instead of a ~40 us NCCL call.
 //       - all-gather of the new basis block: every rank stores its rows directly into every peer's copy of the full
 //         n x b block -- either column-major or already in the MMA-fragment order the block matvec consumes -- so
 //         the stage / all-gather / unstage / pack passes of the NCCL path disappear.
@@ -40,6 +41,17 @@ struct PeerArgs {
   int rank, world;
 };
 
+// where a reduced k x b block goes (Comm::reduce_sum):
+//   mode 0: C(m, j) at C[m + j*ldc]
+//   mode 1: block column `kold..` of a symmetric projected matrix (leading dimension ldc): entry (m, kold+j) is stored
+//           when it lies in the upper triangle and mirrored below the diagonal (what copy + symmetrize_from_upper did)
+struct ReduceOut {
+  int mode;
+  double* C;
+  int64_t ldc;
+  int kold;
+};
+
 // a symmetric segment: the same number of bytes on every rank, every rank holds a mapping of every peer's copy
 struct SymBuf {
   void* local = nullptr;
@@ -64,6 +76,10 @@ class Comm {
 
   // in-place sum over ranks (bit-identical on every rank)
   void allreduce_sum(double* buf, size_t count, cudaStream_t s);
+  // ONE kernel: element (m, j) = sum_z src[z*M*N + m + j*M] (the split-K partials of a tall-skinny product, fixed
+  // order), summed over the ranks, stored per `out`.  Works on a single rank too (then it is the split-K reduction
+  // with the output layout fused in).
+  void reduce_sum(const double* src, int splits, int64_t M, int64_t N, const ReduceOut& out, cudaStream_t s);
   // recv[r*bytes .. (r+1)*bytes) = send of rank r (small payloads; NCCL)
   void allgather(const void* send, void* recv, size_t bytes_per_rank, cudaStream_t s);
   // two segments per rank, send = [a | b]:  recv = [a of rank 0 .. a of rank P-1 | b of rank 0 .. b of rank P-1]
@@ -95,12 +111,15 @@ class Comm {
  private:
   void setup_peer(cudaStream_t s);
   void nccl_allreduce(double* buf, size_t count, cudaStream_t s);
+  void launch_ll(const double* src, int splits, int64_t M, int64_t total, const ReduceOut& out, int64_t gather_seg,
+                 bool exchange, cudaStream_t s);
+  DevBuf<double> nccl_tmp_;  // contiguous staging of reduce_sum on the NCCL transport
   PeerArgs args_for(const SymBuf& b) const;
   int rank_ = 0, world_ = 1;
   void* comm_ = nullptr;
   bool peer_ = false, peer_tried_ = false;
   SymBuf ctl_, slots_;
-  size_t slot_cap_ = 0;  // doubles per (parity, rank) slot
+  size_t slot_cap_ = 0;  // 16-byte lines per (parity, source rank)
   unsigned long long ar_epoch_ = 0, ag_epoch_ = 0;
   void* hbuf_ = nullptr;  // device scratch for the handle exchange
 };

@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(NT) gemm_kernel(int64_t M, int64_t N, int64_t 
                                                   const double* __restrict__ A, int64_t lda,
                                                   const double* __restrict__ B, int64_t ldb, double beta,
                                                   double* __restrict__ C, int64_t ldc, double* __restrict__ ws,
-                                                  int splits) {
+                                                  int splits, int to_ws) {
   __shared__ __align__(16) double As[BK][LDS_];
   __shared__ __align__(16) double Bs[BK][LDS_];
   const int tid = threadIdx.x;
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(NT) gemm_kernel(int64_t M, int64_t N, int64_t 
     __syncthreads();
   }
 
-  if (splits == 1) {
+  if (splits == 1 && !to_ws) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int64_t gj = n0 + tn * 4 + j;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(128) gemm_dmma_kernel(int64_t M, int64_t N, in
                                                         const double* __restrict__ A, int64_t lda,
                                                         const double* __restrict__ B, int64_t ldb, double beta,
                                                         double* __restrict__ C, int64_t ldc, double* __restrict__ ws,
-                                                        int splits) {
+                                                        int splits, int to_ws) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int64_t m0 = (int64_t)blockIdx.x * BM + (warp & 1) * 32;
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(128) gemm_dmma_kernel(int64_t M, int64_t N, in
       for (int c = 0; c < 2; ++c) {
         const int64_t n = n0 + 8 * j + 2 * t + c;
         if (n >= N) continue;
-        if (splits == 1) {
+        if (splits == 1 && !to_ws) {
           double* q = C + m + n * ldc;
           *q = (beta == 0.0) ? alpha * acc[i][j][c] : alpha * acc[i][j][c] + beta * (*q);
         } else {
@@ -227,8 +227,16 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(int64_t M, int64_t N
 }  // namespace
 
 void gemm(cudaStream_t s, bool transA, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
-          const double* B, int64_t ldb, double beta, double* C, int64_t ldc, double* ws, size_t ws_doubles) {
-  if (M <= 0 || N <= 0) return;
+          const double* B, int64_t ldb, double beta, double* C, int64_t ldc, double* ws, size_t ws_doubles,
+          int* partials_out) {
+  if (M <= 0 || N <= 0) {
+    if (partials_out) *partials_out = 0;
+    return;
+  }
+  if (partials_out && (ws == nullptr || ws_doubles < (size_t)M * (size_t)N))
+    DAV_THROW(DAV_ERR_STATE, "gemm: workspace too small for the partials of a %lld x %lld product", (long long)M,
+              (long long)N);
+  const int to_ws = partials_out ? 1 : 0;
   const int64_t gx = ceil_div(M, BM), gy = ceil_div(N, BN);
   int splits = 1;
   // read per call so one process can compare the two implementations (tests, bench A/B)
@@ -249,15 +257,19 @@ void gemm(cudaStream_t s, bool transA, int64_t M, int64_t N, int64_t K, double a
   if (gy > 65535 || splits > 65535) DAV_THROW(DAV_ERR_INVALID, "gemm grid too large");
   dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)splits);
   if (impl == 1 && transA)
-    gemm_dmma_kernel<true><<<grid, 128, 0, s>>>(M, N, K, Kchunk, alpha, A, lda, B, ldb, beta, C, ldc, ws, splits);
+    gemm_dmma_kernel<true><<<grid, 128, 0, s>>>(M, N, K, Kchunk, alpha, A, lda, B, ldb, beta, C, ldc, ws, splits, to_ws);
   else if (impl == 1)
-    gemm_dmma_kernel<false><<<grid, 128, 0, s>>>(M, N, K, Kchunk, alpha, A, lda, B, ldb, beta, C, ldc, ws, splits);
+    gemm_dmma_kernel<false><<<grid, 128, 0, s>>>(M, N, K, Kchunk, alpha, A, lda, B, ldb, beta, C, ldc, ws, splits, to_ws);
   else if (transA)
-    gemm_kernel<true><<<grid, NT, 0, s>>>(M, N, K, Kchunk, alpha, A, lda, B, ldb, beta, C, ldc, ws, splits);
+    gemm_kernel<true><<<grid, NT, 0, s>>>(M, N, K, Kchunk, alpha, A, lda, B, ldb, beta, C, ldc, ws, splits, to_ws);
   else
-    gemm_kernel<false><<<grid, NT, 0, s>>>(M, N, K, Kchunk, alpha, A, lda, B, ldb, beta, C, ldc, ws, splits);
+    gemm_kernel<false><<<grid, NT, 0, s>>>(M, N, K, Kchunk, alpha, A, lda, B, ldb, beta, C, ldc, ws, splits, to_ws);
   CK_LAUNCH();
   ++g_kernel_launches;
+  if (partials_out) {  // the caller reduces the partials itself (Comm::reduce_sum: split-K + ranks + layout)
+    *partials_out = splits;
+    return;
+  }
   if (splits > 1) {
     const int64_t total = M * N;
     const int blocks = (int)ceil_div(total, 64);

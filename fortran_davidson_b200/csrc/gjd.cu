@@ -23,8 +23,10 @@ namespace dav {
 namespace {
 
 constexpr int NCH = 64;  // row chunks of the two-stage column reductions (== vecops.cu NCHUNK)
-constexpr double GJD_RTOL = 1e-8;
-constexpr int GJD_MAXIT = 40;
+// inner (MINRES) stopping rule, relative to ||r_j||: 1e-8 for the usual outer tolerances, tightened with the outer
+// tolerance below that (an outer 1e-12 gets a 1e-12 inner solve and 8 more inner iterations per decade)
+constexpr double GJD_RTOL_MAX = 1e-8;
+constexpr int GJD_MAXIT_BASE = 40;
 constexpr double GJD_DFLOOR = 1e-8;
 
 enum { S_BETA, S_OLDB, S_BETA1, S_DBAR, S_EPSLN, S_OLDEPS, S_PHIBAR, S_CS, S_SN, S_ALFA, S_DELTA, S_GAMMA, S_PHI,
@@ -212,7 +214,10 @@ using namespace dav;
 
 // C <- GJD corrections for all k Ritz pairs.  On entry R holds the residuals and C holds
 // w = (BV | V) * Y (residual_dpr leaves it untouched when no DPR correction is written).
-void dav_solver::gjd_correction(int k, bool gev) {
+void dav_solver::gjd_correction(int k, bool gev, double outer_tolerance) {
+  const double GJD_RTOL = std::min(GJD_RTOL_MAX, std::max(outer_tolerance, 1e-14));
+  const int GJD_MAXIT =
+      GJD_MAXIT_BASE + (GJD_RTOL < GJD_RTOL_MAX ? (int)std::ceil(8.0 * std::log10(GJD_RTOL_MAX / GJD_RTOL)) : 0);
   const size_t nk = (size_t)ldv * (kcap / 2 > 0 ? std::max(kcap / 2, k) : k);
   const int nbuf = 13;
   gjd_buf.alloc(nk * nbuf);
@@ -264,8 +269,7 @@ void dav_solver::gjd_correction(int k, bool gev) {
   for (int itn = 1; itn <= GJD_MAXIT; ++itn) {
     GJD_VEC(PH_A, itn); reduce_to(S_D0);
     GJD_VEC(PH_B, itn);
-    apply(0, a.P, ldv, k, a.AP, ldv);
-    if (gev) apply(1, a.P, ldv, k, a.BP, ldv);
+    apply_both(a.P, k, a.AP, gev ? a.BP : nullptr);  // ONE gather of P feeds A*P and B*P
     GJD_VEC(PH_C, itn); reduce_to(S_D1);
     GJD_VEC(PH_D, itn); reduce_to(S_ALFA);
     GJD_VEC(PH_E, itn); reduce_to(S_WY);

@@ -12,9 +12,12 @@ extern thread_local long long g_kernel_launches;
 //   transA == false : A is M x K (lda)            -- "NN": V*G updates, AV*Y, C*T
 //   transA == true  : A is stored K x M (lda)     -- "TN": projections V^T W (K = local rows)
 // ws: workspace for split-K partials (TN with long K); ws_doubles its capacity.
+// partials_out != nullptr: the product (alpha = 1, beta = 0 implied) is LEFT as *partials_out partial blocks of
+// M x N doubles in ws (ws[z*M*N + m + j*M]) and C is not touched: the caller sums them -- Comm::reduce_sum does that
+// together with the sum over the ranks and the output layout in one kernel.
 void gemm(cudaStream_t s, bool transA, int64_t M, int64_t N, int64_t K, double alpha, const double* A,
           int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, double* ws,
-          size_t ws_doubles);
+          size_t ws_doubles, int* partials_out = nullptr);
 
 // ---- matvec_dmma.cu : the hot kernel.  W(M x b) = A(M x K, lda) * X(K x b)  ---------------------
 // TMA (2D tensor map, 128B swizzle) -> mbarrier pipeline -> FP64 DMMA, persistent stream-K grid.

@@ -561,6 +561,139 @@ __global__ void __launch_bounds__(512) chol_inv_upper_kernel(int b, const double
   if (tid == 0) flag[0] = 0.0;
 }
 
+// Register-tile variant for b <= 128 (the widths of every BASELINE config): T x T threads, T = ceil(b/4), thread
+// (ty, tx) keeps the 4 x 4 tile (rows 4ty.., columns 4tx..) in registers.  Phase 1, right-looking Cholesky: per step
+// ONE barrier -- the owners of row j+1 publish their freshly updated (unscaled) row and the diagonal thread its
+// 1/sqrt(pivot) while everyone else is still applying step j (look-ahead), the update uses row_a * row_c / pivot.
+// Phase 2, R^-1 by the column operations that turn R into I applied to an identity kept in the same registers
+// (X(:,j) /= R(j,j); X(:,c) -= X(:,j) R(j,c)), same look-ahead.  ~2b barrier-separated steps of 16 FMAs per thread
+// instead of b steps of index arithmetic plus a thread-per-column back substitution: 110 -> ~10 us at b = 64.
+__global__ void __launch_bounds__(1024) chol_inv_tile_kernel(int b, const double* __restrict__ G,
+                                                             double* __restrict__ Tout, double* __restrict__ flag) {
+  extern __shared__ __align__(16) double sm[];
+  const int T = (b + 3) >> 2, bp = 4 * T;
+  double* Rs = sm;                       // bp x bp: Rs[j * bp + c] = R(j, c), c >= j
+  double* buf = Rs + (size_t)bp * bp;    // 2 x bp: published row (phase 1) / column (phase 2), double buffered
+  double* rinv_s = buf + 2 * bp;         // bp
+  __shared__ int bad;
+  const int tx = threadIdx.x % T, ty = threadIdx.x / T;
+  const int r0 = 4 * ty, c0 = 4 * tx;
+  double t[4][4];
+  double d0[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int a = r0 + i, c = c0 + jj;
+      t[i][jj] = (a < b && c < b) ? G[min(a, c) + (size_t)max(a, c) * b] : (a == c ? 1.0 : 0.0);
+    }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) d0[i] = t[i][i];  // meaningful on the diagonal threads only
+  if (threadIdx.x == 0) bad = 0;
+  __syncthreads();
+
+  // phase 1 look-ahead: row jn (unscaled) and 1/sqrt(pivot jn)
+  auto publish_row = [&](int jn) {
+    if (ty != (jn >> 2)) return;
+    const int i = jn & 3;
+    double* rb = buf + (jn & 1) * bp;
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii)
+      if (ii == i) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) rb[c0 + jj] = t[ii][jj];
+        if (tx == ty) {
+          const double d = t[ii][ii];
+          // pivot must stay well above the round-off of the eliminations (cond(G) < ~1e12)
+          if (!(d > 1e-12 * fabs(d0[ii])) || !(d0[ii] > 0.0)) {
+            bad = 1;
+            rinv_s[jn] = 0.0;
+          } else {
+            rinv_s[jn] = rsqrt(d);
+          }
+        }
+      }
+  };
+  publish_row(0);
+  for (int j = 0; j < bp; ++j) {
+    __syncthreads();
+    if (bad) break;  // uniform
+    const double* rb = buf + (j & 1) * bp;
+    const double rinv = rinv_s[j];
+    if (ty == (j >> 2)) {
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) Rs[(size_t)j * bp + c0 + jj] = rb[c0 + jj] * rinv;
+    }
+    if (r0 + 3 > j && c0 + 3 > j) {
+      const double dinv = rinv * rinv;
+      double ra[4], rc[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        ra[i] = (r0 + i > j) ? rb[r0 + i] * dinv : 0.0;
+        rc[i] = (c0 + i > j) ? rb[c0 + i] : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) t[i][jj] = fma(-ra[i], rc[jj], t[i][jj]);
+    }
+    if (j + 1 < bp) publish_row(j + 1);
+  }
+  __syncthreads();
+  if (bad) {
+    if (threadIdx.x == 0) flag[0] = 1.0;
+    return;
+  }
+
+  // phase 2: X = R^-1 in the same registers
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) t[i][jj] = (r0 + i == c0 + jj) ? 1.0 : 0.0;
+  auto publish_col = [&](int jn) {  // column jn scaled by 1 / R(jn, jn)
+    if (tx != (jn >> 2)) return;
+    const int jj = jn & 3;
+    const double rinv = rinv_s[jn];
+    double* xb = buf + (jn & 1) * bp;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q == jj) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          t[i][q] *= rinv;
+          xb[r0 + i] = t[i][q];
+        }
+      }
+  };
+  publish_col(0);
+  for (int j = 0; j < bp; ++j) {
+    __syncthreads();
+    if (c0 + 3 > j && r0 <= j) {  // X(a, j) = 0 for a > j
+      const double* xb = buf + (j & 1) * bp;
+      const double* rj = Rs + (size_t)j * bp;
+      double xa[4], rc[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        xa[i] = xb[r0 + i];
+        rc[i] = (c0 + i > j) ? rj[c0 + i] : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) t[i][jj] = fma(-xa[i], rc[jj], t[i][jj]);
+    }
+    if (j + 1 < bp) publish_col(j + 1);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int a = r0 + i, c = c0 + jj;
+      if (a < b && c < b) Tout[a + (size_t)c * b] = (a <= c) ? t[i][jj] : 0.0;
+    }
+  if (threadIdx.x == 0) flag[0] = 0.0;
+}
+
 __global__ void invert_upper_kernel(int k, const double* __restrict__ R, int64_t ld, double* __restrict__ X) {
   // column j of X solves R x = e_j (x_i = 0 for i > j), back substitution
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < k; j += gridDim.x * blockDim.x) {
@@ -734,9 +867,22 @@ void cholesky_upper(cudaStream_t s, int k, double* G, int64_t ld, int* status) {
   ++g_kernel_launches;
 }
 
-bool chol_inv_upper(cudaStream_t s, int b, const double* G, double* T, double* flag, double* gwork,
+bool chol_inv_upper(cudaStream_t s, int b, const double* G, double* T_, double* flag, double* gwork,
                     size_t gwork_doubles) {
+  double* T = T_;
   const int max_smem = device_max_smem_optin();
+  static const bool tile_off = [] { const char* e = std::getenv("DAV_CHOL_TILE"); return e && std::atoi(e) == 0; }();
+  if (b <= 128 && !tile_off) {
+    const int T = (b + 3) / 4, bp = 4 * T;
+    const size_t bytes = ((size_t)bp * bp + 3 * (size_t)bp) * sizeof(double);
+    if (bytes <= (size_t)max_smem - 1024) {
+      ensure_dyn_smem(chol_inv_tile_kernel, max_smem - 1024);
+      chol_inv_tile_kernel<<<1, T * T, bytes, s>>>(b, G, T_, flag);
+      CK_LAUNCH();
+      ++g_kernel_launches;
+      return true;
+    }
+  }
   ensure_dyn_smem(chol_inv_upper_kernel, max_smem - 1024);
   const size_t tri2 = (size_t)b * (b + 1);
   const size_t bytes = (tri2 + b) * sizeof(double);

@@ -32,7 +32,7 @@ using namespace dav;
 namespace {
 enum { SPAN_MATVEC = 0, SPAN_RR = 1, SPAN_ORTH = 2, SPAN_RESID = 3, SPAN_PROJ = 4, SPAN_INIT = 5, SPAN_TOTAL = 6,
        SPAN_GATHER = 7, SPAN_OUT = 8, SPAN_COMM = 9 };
-constexpr int EV_POOL = 1024;
+constexpr int EV_POOL = 1 << 16;  // events; beyond it spans are dropped and counted (stats.spans_dropped)
 }  // namespace
 
 dav_solver::dav_solver(int device_, int rank, int world, const void* id128) : device(device_) {
@@ -266,7 +266,10 @@ int dav_solver::begin_span(int kind) {
   static const bool no_spans = [] { const char* e = std::getenv("DAV_NO_SPANS"); return e && std::atoi(e) != 0; }();
   if (no_spans && kind != SPAN_TOTAL) return -1;
   if (ev_used + 2 > (int)ev_pool.size()) {
-    if ((int)ev_pool.size() >= EV_POOL) return -1;
+    if ((int)ev_pool.size() >= EV_POOL) {
+      stats.spans_dropped += 1;
+      return -1;
+    }
     for (int i = 0; i < 64; ++i) {
       cudaEvent_t ev;
       CK(cudaEventCreate(&ev));
@@ -382,6 +385,26 @@ void dav_solver::count_matvec(int b) {
 }
 
 // NB: every term is identical on all ranks (the ranks must take the same branch around a collective)
+void dav_solver::apply_both(const double* Xlocal, int b, double* WA, double* WB) {
+  const bool packed = packed_gather_usable() && xpk.bytes >= matvec_packed_doubles(n, b) * 8;
+  int64_t ldf = 0;
+  const double* Xf = nullptr;
+  const int spg = begin_span(SPAN_GATHER);
+  if (packed) {  // every rank stores its rows of X straight into every peer's packed operand of the matvec
+    comm.gather_rows_packed(Xlocal, ldv, nl, row0, n, matvec_kpad(n), b, xpk, stream);
+    stats.collectives += 1;
+  } else {
+    Xf = gather_rows(Xlocal, ldv, b, &ldf);  // one exchange for both matrices
+  }
+  end_span(spg);
+  double* Ws[2] = {WA, WB};
+  for (int w = 0; w < 2; ++w) {
+    if (!Ws[w]) continue;
+    if (packed) apply_packed(w, b, Ws[w], ldv);
+    else apply_full(w, Xf, ldf, b, Ws[w], ldv);
+  }
+}
+
 bool dav_solver::packed_gather_usable() const {
   if (!comm.peer() || matvec_impl == DAV_MATVEC_SIMT || !matvec_dmma_supported()) return false;
   if ((int64_t)(comm.world() - 1) * chunk >= n) return false;  // some rank owns no rows (and has no plan)
@@ -410,6 +433,7 @@ void dav_solver::alloc_work(int lowest, int kcap_) {
   jscratch.alloc(sym_eigh_scratch_doubles(kcap));
   partial.alloc((size_t)kcap * 64);
   gemm_ws.alloc(std::max<size_t>(kk * 64, (size_t)1 << 22));
+  gemm_ws2.alloc(std::max<size_t>(kk * 16, (size_t)1 << 20));
   small.alloc(16);
   status.alloc(4);
   flags.alloc(kcap);
@@ -468,14 +492,28 @@ void dav_solver::rayleigh_ritz(int k, bool gev) {
   end_span(sp);
 }
 
+// C(M x N) = sum over ranks of A(:, 0:M)^T B(:, 0:N) (local rows of two n x . blocks), stored per `out`
+void dav_solver::tn_reduce(int M, int N, const double* A, const double* B, dav::DevBuf<double>& ws,
+                           const dav::ReduceOut& out) {
+  int parts = 0;
+  gemm(stream, true, M, N, nl, 1.0, A, ldv, B, ldv, 0.0, nullptr, 0, ws.p, ws.n, &parts);
+  const int sp = comm.active() ? begin_span(SPAN_COMM) : -1;
+  if (parts == 0) {  // a rank without rows contributes zeros
+    fill_zero(stream, ws.p, (size_t)M * N);
+    parts = 1;
+  }
+  comm.reduce_sum(ws.p, parts, M, N, out, stream);
+  end_span(sp);
+  if (comm.active()) stats.collectives += 1;
+}
+
 // P(0:k, 0:k) = V^T W for the whole basis (initial step and after a collapse; davidson.f90:131,223)
 void dav_solver::full_projection(int which, int k) {
   const int sp = begin_span(SPAN_PROJ);
   double* W = which ? BV.p : AV.p;
   double* P = which ? Bp.p : Ap.p;
-  gemm(stream, true, k, k, nl, 1.0, V.p, ldv, W, ldv, 0.0, G.p, k, gemm_ws.p, gemm_ws.n);
-  allreduce(G.p, (size_t)k * k);
-  copy_matrix(stream, k, k, G.p, k, P, kcap);
+  // product -> split-K partials; ONE kernel sums the partials and the ranks and writes P
+  tn_reduce(k, k, V.p, W, gemm_ws, dav::ReduceOut{0, P, kcap, 0});
   end_span(sp);
 }
 
@@ -485,10 +523,9 @@ void dav_solver::project_new_block(int which, int kold, int b) {
   double* W = (which ? BV.p : AV.p) + (size_t)kold * ldv;
   double* P = which ? Bp.p : Ap.p;
   const int kn = kold + b;
-  gemm(stream, true, kn, b, nl, 1.0, V.p, ldv, W, ldv, 0.0, G.p, kn, gemm_ws.p, gemm_ws.n);
-  allreduce(G.p, (size_t)kn * b);
-  copy_matrix(stream, kn, b, G.p, kn, P + (size_t)kold * kcap, kcap);
-  symmetrize_from_upper(stream, kn, P, kcap);
+  // product -> split-K partials; ONE kernel sums the partials and the ranks and writes the block column of P and
+  // its mirror image (only the upper triangle is ever read: DSYEV / DSYGV 'U', lapack_wrapper.f90:59,73)
+  tn_reduce(kn, b, V.p, W, gemm_ws, dav::ReduceOut{1, P, kcap, kold});
   end_span(sp);
 }
 
@@ -558,15 +595,14 @@ bool dav_solver::orthonormalize_block_pip(int b, int kold) {
     pip_finish(stream, kold, b, U.p, D.p, Tm.p, Z.p);
     gemm(stream, false, kold, b, b, -1.0, G.p, kb, Tm.p, b, 0.0, Z.p, kb, nullptr, 0);  // rows 0..k: -H Tm
   };
-  // pass 1: [V C]^T C in one product, C1 = [V C] M -> T
-  gemm(stream, true, kb, b, nl, 1.0, V.p, ldv, Vnew, ldv, 0.0, G.p, kb, gemm_ws.p, gemm_ws.n);
-  allreduce(G.p, (size_t)kb * b);
+  // pass 1: [V C]^T C in one product (split-K partials summed over K and over the ranks by one kernel),
+  // C1 = [V C] M -> T
+  tn_reduce(kb, b, V.p, Vnew, gemm_ws, dav::ReduceOut{0, G.p, kb, 0});
   small_ops(0);
   gemm(stream, false, nl, b, kb, 1.0, V.p, ldv, Z.p, kb, 0.0, T.p, ldv, nullptr, 0);
-  // pass 2: H = V^T C1, C1^T C1 (two products into one buffer, one all-reduce)
-  gemm(stream, true, kold, b, nl, 1.0, V.p, ldv, T.p, ldv, 0.0, G.p, kb, gemm_ws.p, gemm_ws.n);
-  gemm(stream, true, b, b, nl, 1.0, T.p, ldv, T.p, ldv, 0.0, G.p + kold, kb, gemm_ws.p, gemm_ws.n);
-  allreduce(G.p, (size_t)kb * b);
+  // pass 2: H = V^T C1 and C1^T C1 into the rows 0..kold / kold.. of the same block
+  tn_reduce(kold, b, V.p, T.p, gemm_ws, dav::ReduceOut{0, G.p, kb, 0});
+  tn_reduce(b, b, T.p, T.p, gemm_ws2, dav::ReduceOut{0, G.p + kold, kb, 0});
   small_ops(1);
   double h[8];
   CK(cudaMemcpyAsync(h, small.p, sizeof(h), cudaMemcpyDeviceToHost, stream));
@@ -742,28 +778,13 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
       if ((int64_t)2 * k > n || 2 * k > kcap)
         DAV_THROW(DAV_ERR_BASIS_TOO_LARGE, "basis of %d columns cannot be expanded inside an n = %lld problem", k,
                   (long long)n);
-      if (method == DAV_METHOD_GJD) gjd_correction(k, gev);           // C <- GJD corrections
+      if (method == DAV_METHOD_GJD) gjd_correction(k, gev, tolerance);  // C <- GJD corrections
       double* Q = V.p + (size_t)k * ldv;
       copy_matrix(stream, nl, k, C.p, ldv, Q, ldv);                   // [V | C] contiguous
       if (!orthonormalize_block_pip(k, k))                            // steps 6-7 (:210-213)
         orthonormalize_block(Q, k, k, Q);
-      const bool packed = packed_gather_usable() && xpk.bytes >= matvec_packed_doubles(n, k) * 8;
-      int64_t ldf = 0;
-      const double* Qf = nullptr;
-      const int spg = begin_span(SPAN_GATHER);
-      if (packed) {  // every rank stores its rows of Q straight into every peer's packed operand of the matvec
-        comm.gather_rows_packed(Q, ldv, nl, row0, n, matvec_kpad(n), k, xpk, stream);
-        stats.collectives += 1;
-      } else {
-        Qf = gather_rows(Q, ldv, k, &ldf);                            // one all-gather for both matrices
-      }
-      end_span(spg);
-      for (int w = 0; w < (gev ? 2 : 1); ++w) {
-        double* W = (w ? BV.p : AV.p) + (size_t)k * ldv;
-        if (packed) apply_packed(w, k, W, ldv);                       // the block matvec
-        else apply_full(w, Qf, ldf, k, W, ldv);
-        project_new_block(w, k, k);
-      }
+      apply_both(Q, k, AV.p + (size_t)k * ldv, gev ? BV.p + (size_t)k * ldv : nullptr);  // the block matvec(s)
+      for (int w = 0; w < (gev ? 2 : 1); ++w) project_new_block(w, k, k);
       k *= 2;
     } else {                                                          // collapse (:218)
       sp = begin_span(SPAN_ORTH);
@@ -811,6 +832,7 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
     }
   }
   stats.kernel_launches = (int)(g_kernel_launches - launches0);
+  stats.peer_transport = comm.peer() ? 1 : 0;
 
   if (converged) {
     *iters = it;

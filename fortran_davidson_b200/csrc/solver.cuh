@@ -40,7 +40,7 @@ struct dav_solver {
   // peer transport (comm.cuh): every rank's copy of the gathered block, written by all ranks directly
   dav::SymBuf xsym;  // n x b column-major (generic consumers: matrix-free operators, output, SIMT kernels)
   dav::SymBuf xpk;   // packed MMA-fragment order (the dense TMA/DMMA matvec)
-  dav::DevBuf<double> Ap, Bp, Y, theta, G, U, sv, D, Tm, S1, S2, Z, jscratch, norms2, partial, gemm_ws, small;
+  dav::DevBuf<double> Ap, Bp, Y, theta, G, U, sv, D, Tm, S1, S2, Z, jscratch, norms2, partial, gemm_ws, gemm_ws2, small;
   dav::DevBuf<int> status, flags, gjd_active;
   dav::DevBuf<double> gjd_buf, gjd_st;
   dav::DevBuf<int64_t> idx, topk_idx;
@@ -82,6 +82,8 @@ struct dav_solver {
   // W = M_which * X for the block last gathered with comm.gather_rows_packed into xpk
   void apply_packed(int which, int b, double* W, int64_t ldw);
   void count_matvec(int b);
+  // WA = M_0 * X and (WB != nullptr) WB = M_1 * X for a row-sharded block X (nl x b, ldv): one exchange of X
+  void apply_both(const double* Xlocal, int b, double* WA, double* WB);
 
   int solve(int lowest, int method, int max_iterations, double tolerance, int max_dim_sub, double* eigenvalues,
             double* eigenvectors, int64_t ldvec, int* iters);
@@ -91,8 +93,9 @@ struct dav_solver {
   void rayleigh_ritz(int k, bool gev);
   void orthonormalize_block(double* Cblk, int b, int kold, double* dest);
   bool orthonormalize_block_pip(int b, int kold);
-  void gjd_correction(int k, bool gev);
+  void gjd_correction(int k, bool gev, double outer_tolerance);
   void project_new_block(int which, int kold, int b);
+  void tn_reduce(int M, int N, const double* A, const double* B, dav::DevBuf<double>& ws, const dav::ReduceOut& out);
   void full_projection(int which, int k);
   void allreduce(double* buf, size_t count);
   void allgather(const void* send, void* recv, size_t bytes_per_rank);

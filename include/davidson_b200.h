@@ -168,7 +168,9 @@ typedef struct {
   double gather_ms;         /* all-gather of the new basis block over the ranks (+ staging kernels) */
   double output_ms;         /* Ritz vectors of the result: V*y, gather, copy to the host */
   double comm_ms;           /* time inside NCCL collectives (nested in the phases above; includes waiting for peers) */
-  int collectives;          /* NCCL calls of the solve */
+  int collectives;          /* inter-GPU exchanges of the solve (own peer-memory kernels or NCCL calls) */
+  int spans_dropped;        /* phase spans not timed because the event pool was exhausted (0: the *_ms are complete) */
+  int peer_transport;       /* 1: the exchanges were the library's peer-memory kernels, 0: NCCL / single GPU */
 } dav_stats_t;
 int dav_get_stats(dav_solver_t* h, dav_stats_t* out);
 
@@ -192,6 +194,11 @@ int dav_bench_fp64_pipe(dav_solver_t* h, int reps, double* dmma_tflops);
  * tall-skinny GEMM kernel of the library; returns max |W_matvec - W_gemm| and max |W_gemm|.  Lets one GPU validate the
  * multi-GPU tile shapes. */
 int dav_debug_matvec_rect(int device, int64_t m, int64_t k, int b, double* max_abs_diff, double* scale);
+
+/* Test entry of the b x b Cholesky + triangular inverse of the block orthonormalisation (host pointers): g = b x b
+ * symmetric positive definite, column-major, upper triangle read; t <- R^-1 with g = R^T R (upper triangular, zeros
+ * below); *flag = 1.0 when a pivot was not safely positive (t is then undefined); *ms (may be NULL) = kernel time. */
+int dav_debug_chol_inv(int b, const double* g, double* t, double* flag, float* ms);
 
 /* Self-check and timing of the inter-GPU exchanges of a distributed handle (collective: every rank calls it with the
  * same arguments).  kind 0 = all-reduce on the transport in use (peer-memory kernel when the GPUs map each other,

@@ -1,0 +1,166 @@
+"""GPU parity tests added in round 2: wide expansion blocks, the in-solver widths 32 / 64 / 128 at lowest = 16,
+GJD iteration-count equality on a case with >= 4 outer iterations, the register-tile Cholesky + inverse of the block
+orthonormalisation, and the multi-GPU parity check under torchrun when the box has more than one GPU.
+Tolerances are BASELINE.json's: eigenvalues 1e-10 relative, eigenvectors up to sign 1e-8, residual <= tol."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import fortran_davidson_b200 as fd
+from fortran_davidson_b200._lib import check, dp, lib
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+EV_RTOL = 1e-10
+VEC_ATOL = 1e-8
+
+
+def _solve_handle(A, B, L, method, max_it, tol, md):
+    s = fd.DavidsonSolver()
+    s.upload(0, A)
+    if B is not None:
+        s.upload(1, B)
+    ev, vec, iters = s.solve(L, method, max_it, tol, md)
+    st = s.stats()
+    trace = list(st.trace_k[:st.trace_len])
+    s.close()
+    return ev, vec, iters, trace
+
+
+def _check_against_oracle(A, B, ev, vec, r, tol):
+    assert np.abs(ev - r.eigenvalues).max() / np.abs(r.eigenvalues).max() < EV_RTOL
+    Bm = B if B is not None else None
+    for j in range(len(ev)):
+        bv = Bm @ r.eigenvectors[:, j] if Bm is not None else r.eigenvectors[:, j]
+        sg = np.sign(vec[:, j] @ bv)
+        assert np.abs(sg * vec[:, j] - r.eigenvectors[:, j]).max() < VEC_ATOL
+        bvec = Bm @ vec[:, j] if Bm is not None else vec[:, j]
+        assert np.linalg.norm(A @ vec[:, j] - ev[j] * bvec) < max(tol, 1e-8)
+
+
+# ---------------------------------------------------------------- b x b Cholesky + inverse (block orthonormalisation)
+@pytest.mark.parametrize("b", [1, 3, 4, 5, 31, 32, 64, 100, 128, 129, 150, 169, 170, 200, 256])
+def test_chol_inv_upper_matches_numpy(b):
+    rng = np.random.default_rng(b)
+    M = rng.standard_normal((b + 5, b))
+    G = np.asfortranarray(M.T @ M / (b + 5) + 0.5 * np.eye(b))
+    # only the upper triangle may be read: poison the strictly lower part
+    Gp = np.asfortranarray(np.triu(G) + np.tril(np.full((b, b), 7.5), -1))
+    T = np.zeros((b, b), order="F")
+    flag = C.c_double(-1.0)
+    ms = C.c_float(0.0)
+    check(lib().dav_debug_chol_inv(C.c_int(b), dp(Gp), dp(T), C.byref(flag), C.byref(ms)))
+    assert flag.value == 0.0
+    R = np.linalg.cholesky(G).T  # upper, G = R^T R
+    ref = np.linalg.inv(R)
+    assert np.abs(np.tril(T, -1)).max() == 0.0 if b > 1 else True
+    assert np.abs(T - ref).max() <= 1e-12 * np.abs(ref).max() * max(1.0, np.linalg.cond(G))
+    assert np.abs(T.T @ G @ T - np.eye(b)).max() < 1e-12
+
+
+@pytest.mark.parametrize("b", [8, 64, 128, 200])
+def test_chol_inv_upper_flags_unsafe_pivot(b):
+    rng = np.random.default_rng(1)
+    M = rng.standard_normal((b, b - 1))  # rank b-1: the last pivot is round-off
+    G = np.asfortranarray(M @ M.T)
+    T = np.zeros((b, b), order="F")
+    flag = C.c_double(-1.0)
+    check(lib().dav_debug_chol_inv(C.c_int(b), dp(G), dp(T), C.byref(flag), None))
+    assert flag.value == 1.0
+
+
+# ---------------------------------------------------------------- the in-solver widths of configs[2]: 32, 64, 128
+def test_dense_lowest16_widths_32_64_128_against_oracle():
+    """lowest = 16 (BASELINE.json configs[2] at n = 20,000 instead of 100,000): the expansion blocks are 32 and 64
+    columns wide, the Rayleigh-Ritz problems 32 / 64 / 128 -- the very kernels of the headline solve."""
+    n, L = 20000, 16
+    s = fd.DavidsonSolver()
+    s.generate_diagonal_dominant(0, n, 1e-4, None, 0)
+    ev, vec, iters = s.solve(L, "DPR", 1000, 1e-8, None)
+    st = s.stats()
+    trace = list(st.trace_k[:st.trace_len])
+    s.close()
+    A = orc.generate_diagonal_dominant(n, 1e-4, None, 0)
+    r = orc.generalized_eigensolver(A, L, "DPR", 1000, 1e-8, None)
+    assert iters == r.iters == 3 and trace == [32, 64, 128]
+    _check_against_oracle(A, None, ev, vec, r, 1e-8)
+
+
+def test_dense_lowest16_harder_input_widths_up_to_128():
+    """Same widths on an input that needs the 128-column expansion too (sparsity 2e-2: 5 iterations, a collapse)."""
+    n, L = 6000, 16
+    A = orc.generate_diagonal_dominant(n, 2e-2, None, 3)
+    r = orc.generalized_eigensolver(A, L, "DPR", 1000, 1e-8, None)
+    ev, vec, iters, trace = _solve_handle(A, None, L, "DPR", 1000, 1e-8, None)
+    assert abs(iters - r.iters) <= 1 and trace[:4] == [32, 64, 128, 256] == [int(k) for k in r.trace_k][:4]
+    assert max(trace) >= 256  # the k = 128 -> 256 expansion (b = 128) ran
+    _check_against_oracle(A, None, ev, vec, r, 1e-8)
+
+
+# ---------------------------------------------------------------- wide expansion blocks (b >= 170: ADVICE r1, high)
+def test_wide_first_expansion_block_lowest_90():
+    """lowest = 90: the first expansion block already has 180 columns -- wider than the shared-memory Cholesky of
+    the block orthonormalisation can hold; the reference's Householder QR has no such limit."""
+    n, L = 2500, 90
+    A = orc.generate_diagonal_dominant(n, 1e-3, None, 5)
+    r = orc.generalized_eigensolver(A, L, "DPR", 200, 1e-8, None)
+    ev, vec, iters, trace = _solve_handle(A, None, L, "DPR", 200, 1e-8, None)
+    assert abs(iters - r.iters) <= 1
+    assert trace[:2] == [180, 360]
+    _check_against_oracle(A, None, ev, vec, r, 1e-8)
+
+
+def test_wide_third_expansion_block_lowest_32():
+    """lowest = 32 with the default max_dim_sub = 320: a solve that is still unconverged at k = 256 expands by a
+    256-column block (configs[4] only avoids it by converging earlier)."""
+    n, L = 4000, 32
+    A = orc.generate_diagonal_dominant(n, 4e-2, None, 6)
+    r = orc.generalized_eigensolver(A, L, "DPR", 200, 1e-9, None)
+    ev, vec, iters, trace = _solve_handle(A, None, L, "DPR", 200, 1e-9, None)
+    assert [int(k) for k in r.trace_k][:4] == [64, 128, 256, 512], r.trace_k
+    assert trace[:4] == [64, 128, 256, 512]
+    assert abs(iters - r.iters) <= 1
+    _check_against_oracle(A, None, ev, vec, r, 1e-9)
+
+
+# ---------------------------------------------------------------- GJD: iteration counts equal on >= 4 iterations
+@pytest.mark.parametrize("gev", [False, True])
+def test_gjd_iteration_count_equal_on_longer_runs(gev):
+    n, sp, L, md, tol = 700, 1e-2, 3, 10, 1e-9
+    A = orc.generate_diagonal_dominant(n, sp, None, 0)
+    B = orc.generate_diagonal_dominant(n, sp, 1.0, 1) if gev else None
+    r = orc.generalized_eigensolver(A, L, "GJD", 200, tol, md, B)
+    assert r.iters >= 4
+    ev, vec, iters, trace = _solve_handle(A, B, L, "GJD", 200, tol, md)
+    assert iters == r.iters, (iters, r.iters)
+    assert trace == [int(k) for k in r.trace_k]
+    _check_against_oracle(A, B, ev, vec, r, tol)
+
+
+# ---------------------------------------------------------------- multi-GPU parity (collected; skipped on 1 GPU)
+def _visible_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("script", ["dist_collectives_check.py", "dist_gpu_check.py"])
+def test_sharded_solver_parity_under_torchrun(script):
+    """Spawns tests/<script> under torchrun with min(visible GPUs, 8) ranks: the row-block sharded solver (peer-memory
+    exchanges) against the oracle on every rank -- iteration counts, eigenvalues 1e-10, eigenvectors 1e-8."""
+    ng = min(_visible_gpus(), 8)
+    if ng < 2:
+        pytest.skip("one GPU visible: the sharded path needs >= 2 (the driver's scaling run covers it)")
+    port = 29600 + (os.getpid() % 200)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(ng),
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", script)]
+    if script == "dist_collectives_check.py":
+        cmd.append("20000")
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    assert "_CHECK_PASSED world=%d" % ng in p.stdout
