@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--tol", type=float, default=1e-8)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-other", action="store_true", help="skip the attached other_configs (configs[1], [3], long run)")
+    ap.add_argument("--with-free", action="store_true", help="also attach configs[4] (matrix-free n=2M) below 8 GPUs")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--matvec-impl", type=int, default=0)
     # the other BASELINE.json configs (profiles only; the driver runs the default = configs[2])
@@ -122,46 +124,93 @@ def measured_traffic(args, b):
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(args, steps, warmup, budget_s):
-    """Times the oracle (CPU restatement of the reference + real LAPACK) on the host cores on a bounded
-    sample: same generator / lowest / max_dim / tolerance at a smaller n, extrapolated ~ n^2."""
+def mem_available_gb():
+    for ln in open("/proc/meminfo"):
+        if ln.startswith("MemAvailable"):
+            return float(ln.split()[1]) * 1e-6
+    return 0.0
+
+
+def oracle_solve_timed(args, n_s, repeats):
+    """`repeats` timed solves of the oracle (CPU restatement of the reference + real LAPACK) at size n_s with the
+    workload's own generator / lowest / max_dim / tolerance, on all host cores."""
     from oracle import oracle as orc
     cores = os.cpu_count() or 1
     orc.set_num_threads(cores)
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    per_solve = budget_s / max(1, steps + warmup)
-    # ~20 s at n = 20,000 on 16 cores (k DGEMVs per iteration stream A k times), cost ~ n^2
-    n_s = int(min(args.n, max(4000, 20000 * (per_solve / 20.0) ** 0.5)) // 1000 * 1000)
-    n_s = max(min(n_s, 20000, args.n), min(args.n, 2000))
     A = orc.generate_diagonal_dominant(n_s, args.sparsity, None, 0)
     md = args.max_dim or None
-    times = []
-    r = None
-    for i in range(warmup + steps):
+    times, r = [], None
+    for _ in range(repeats):
         t0 = time.perf_counter()
         r = orc.generalized_eigensolver(A, args.lowest, "DPR", 1000, args.tol, md)
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-    t_sample = sum(times) / len(times)
+        times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), r, cores
+
+
+def cpu_reference_run(args, budget_s, full_size):
+    """The oracle on the host cores.  full_size=True (the `--impl reference` arm): ONE measured solve of the very
+    workload (n = args.n) when the host has the RAM for the matrix -- no extrapolation; otherwise the largest n
+    that fits, extrapolated ~ n^2 and labelled as such.  full_size=False (the in-arm `cpu_baseline`): a bounded
+    sample (same generator / lowest / max_dim / tolerance at n <= 20,000, ~5-25 s) extrapolated ~ n^2."""
+    what = ("oracle/ (C++ restatement of davidson.f90 + scipy OpenBLAS LAPACK; no Fortran compiler in the image, so "
+            "the reference itself cannot be built)")
+    if full_size:
+        avail = mem_available_gb()
+        n_s = args.n
+        if 8e-9 * n_s * n_s * 1.05 + 4.0 > avail:
+            n_s = int((max(avail - 4.0, 1.0) * 0.9 / 8e-9) ** 0.5) // 1000 * 1000
+        t_sample, r, cores = oracle_solve_timed(args, n_s, 1)
+        reps = 1
+    else:
+        n_s = int(min(args.n, max(4000, 20000 * (budget_s / 20.0) ** 0.5)) // 1000 * 1000)
+        n_s = max(min(n_s, 20000, args.n), min(args.n, 2000))
+        t_sample, r, cores = oracle_solve_timed(args, n_s, 1)
+        reps = 1
     scale = (args.n / n_s) ** 2
-    return {"value": t_sample * scale, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": ("oracle/ (C++ restatement of davidson.f90 + scipy OpenBLAS LAPACK; no Fortran compiler in the "
-                       "image, so the reference itself cannot be built): full solve at n=%d, lowest=%d, DPR, %d "
-                       "iterations, %.3f s measured (mean of %d), extrapolated x(n/n_sample)^2 = x%.1f to n=%d"
-                       % (n_s, args.lowest, r.iters, t_sample, len(times), scale, args.n)),
-            "sample_n": n_s, "sample_seconds": t_sample, "sample_iters": int(r.iters), "extrapolation_factor": scale}
+    out = {"value": t_sample * scale, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": ("%s: full solve at n=%d, lowest=%d, DPR, %d iterations, %.3f s measured (%d solve)%s"
+                      % (what, n_s, args.lowest, r.iters, t_sample, reps,
+                         "" if n_s == args.n else ", extrapolated x(n/n_sample)^2 = x%.1f to n=%d" % (scale, args.n))),
+           "sample_n": n_s, "sample_seconds": t_sample, "sample_iters": int(r.iters), "extrapolation_factor": scale,
+           "eigenvalue0": float(r.eigenvalues[0])}
+    return out
+
+
+def golden_full_size():
+    """tests/golden/config2_n100k_oracle.json: the oracle's full-size run of configs[2] (made on a GPU box host by
+    tests/golden/make_golden_n100k.py)."""
+    p = os.path.join(ROOT, "tests", "golden", "config2_n100k_oracle.json")
+    return json.load(open(p)) if os.path.exists(p) else None
+
+
+def is_headline(args):
+    return (args.n == 100000 and args.lowest == 16 and args.method == "DPR" and not args.gev and not args.free
+            and args.sparsity == 1e-4 and args.tol == 1e-8 and not args.max_dim)
 
 
 def run_reference(args):
+    """`--impl reference`: rank 0 times ONE full-size solve of the workload with the oracle on the host cores (the
+    line says steps = 1, warmup = 0: a solve takes ~2 minutes, K of them would not fit the run), then the bounded
+    n = 20,000 sample the GPU arm's `cpu_baseline` uses, as a secondary field."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_reference_run(args, args.steps, args.warmup, budget_s=150.0)
-    line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": cb["value"] * 1e3, "higher_is_better": False, "scaling": "strong",
+    cb = cpu_reference_run(args, 0.0, full_size=True)
+    try:
+        small = cpu_reference_run(args, 20.0, full_size=False) if args.n > 20000 else None
+    except Exception as ex:
+        small = {"error": repr(ex)[:200]}
+    g = golden_full_size() if is_headline(args) else None
+    if g is not None and cb["sample_n"] == args.n:
+        cb["matches_committed_golden"] = bool(cb["sample_iters"] == g["iters"]
+                                              and abs(cb["eigenvalue0"] - g["eigenvalues"][0]) <= 1e-12)
+    cb["secondary_sample"] = small
+    line = {"metric": metric_name(args), "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": 1,
+            "warmup": 0, "steps_requested": args.steps, "warmup_requested": args.warmup,
+            "ms_per_step": cb["value"] * 1e3, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": workload_config(args, 1), "cpu_baseline": cb,
+            "config": workload_config(args, args.gpus), "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -202,115 +251,149 @@ def workload_config(args, n_gpus):
 
 
 # ------------------------------------------------------------------------------------------------
-def main():
-    args = parse()
-    if args.impl == "reference":
-        run_reference(args)
-        return
+class Ctx:
+    """Process-wide plumbing of one bench run (one process per GPU)."""
 
-    import numpy as np
-    import torch
-    import torch.distributed as dist
+    def __init__(self, args):
+        import numpy as np
+        import torch
+        import torch.distributed as dist
 
-    import fortran_davidson_b200 as fd
+        import fortran_davidson_b200 as fd
+        self.np, self.torch, self.dist, self.fd, self.args = np, torch, dist, fd, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world > 1:
+            raise SystemExit("--gpus %d does not match WORLD_SIZE %d" % (args.gpus, self.world))
+        torch.cuda.set_device(self.local_rank)
+        self.distributed = self.world > 1
+        if self.distributed:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            ids = [fd.DavidsonSolver.unique_id() if self.rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            self.solver = fd.DavidsonSolver(self.local_rank, self.rank, self.world, ids[0])
+        else:
+            self.solver = fd.DavidsonSolver(self.local_rank)
+        self.solver.set_matvec_impl(args.matvec_impl)
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit("--gpus %d does not match WORLD_SIZE %d" % (args.gpus, world))
-    torch.cuda.set_device(local_rank)
-    distributed = world > 1
-    if distributed:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        ids = [fd.DavidsonSolver.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        solver = fd.DavidsonSolver(local_rank, rank, world, ids[0])
-    else:
-        solver = fd.DavidsonSolver(local_rank)
-    solver.set_matvec_impl(args.matvec_impl)
+    def barrier(self):
+        if self.distributed:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    def barrier():
-        if distributed:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if not distributed:
+    def max_over_ranks(self, x):
+        if not self.distributed:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    n, L = args.n, args.lowest
-    md = args.max_dim or None
+    def sum_over_ranks(self, arr):
+        if not self.distributed:
+            return arr
+        t = self.torch.tensor(arr, dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t)
+        return t.cpu().numpy()
+
+
+def load_workload(cx, w):
+    """Puts the matrices / operators of workload `w` (an argparse-like namespace) into the solver, device-generated."""
+    s, fd = cx.solver, cx.fd
+    s.clear(0)
+    s.clear(1)
+    cx.torch.cuda.empty_cache()
     t0 = time.perf_counter()
-    if args.free:
-        solver.set_operator(0, n, fd.OP_BENCHMARK_MTX)
-        solver.set_operator(1, n, fd.OP_IDENTITY)
+    if w.free:
+        s.set_operator(0, w.n, fd.OP_BENCHMARK_MTX)
+        s.set_operator(1, w.n, fd.OP_IDENTITY)
     else:
-        solver.generate_diagonal_dominant(0, n, args.sparsity, None, 0)
-        if args.gev:
-            solver.generate_diagonal_dominant(1, n, args.sparsity, 1.0, 1)
-    barrier()
-    gen_s = time.perf_counter() - t0
+        s.generate_diagonal_dominant(0, w.n, w.sparsity, None, 0)
+        if w.gev:
+            s.generate_diagonal_dominant(1, w.n, w.sparsity, 1.0, 1)
+    cx.barrier()
+    return time.perf_counter() - t0
 
-    # ---- warm-up
-    for _ in range(args.warmup):
-        ev, _vec, iters = solver.solve(L, args.method, 1000, args.tol, md, want_vectors=True, pinned=True, local=distributed)
 
-    # ---- timed region: exactly K solves, barrier + synchronize on both sides, device time = CUDA events on the
-    # solver's own stream (dav_stats_t.solve_ms), max over ranks
+def timed_solves(cx, w, steps, warmup):
+    """`warmup` untimed + exactly `steps` timed solves, barrier + synchronize on both sides; device time = CUDA events
+    on the solver's own stream (dav_stats_t.solve_ms), max over ranks."""
+    s = cx.solver
+    md = w.max_dim or None
+    kw = dict(want_vectors=True, pinned=True, local=cx.distributed)
+    for _ in range(warmup):
+        s.solve(w.lowest, w.method, 1000, w.tol, md, **kw)
     dev_ms, mv_ms, mv_launch, launches = [], [], [], []
-    per_launch = []
-    barrier()
-    with ClockSampler(local_rank) as clocks:
+    cx.barrier()
+    with ClockSampler(cx.local_rank) as clocks:
         w0 = time.perf_counter()
-        for _ in range(args.steps):
-            ev, vec, iters = solver.solve(L, args.method, 1000, args.tol, md, want_vectors=True, pinned=True, local=distributed)
-            st = solver.stats()
+        for _ in range(steps):
+            ev, vec, iters = s.solve(w.lowest, w.method, 1000, w.tol, md, **kw)
+            st = s.stats()
             dev_ms.append(st.solve_ms)
             mv_ms.append(st.matvec_ms)
             mv_launch.append(st.matvec_launches)
             launches.append(st.kernel_launches)
-        barrier()
-        wall_ms = (time.perf_counter() - w0) * 1e3 / args.steps
-    st = solver.stats()
-    ms_per_step = max_over_ranks(sum(dev_ms) / len(dev_ms))
-    wall_ms = max_over_ranks(wall_ms)
-    value = ms_per_step * 1e-3
+        cx.barrier()
+        wall_ms = (time.perf_counter() - w0) * 1e3 / steps
+    st = s.stats()
+    return {"ms_per_step": cx.max_over_ranks(sum(dev_ms) / len(dev_ms)), "wall_ms": cx.max_over_ranks(wall_ms),
+            "matvec_ms": cx.max_over_ranks(sum(mv_ms) / len(mv_ms)), "matvec_launches": int(mv_launch[-1]),
+            "launches": int(sum(launches) / len(launches)), "ev": ev, "vec": vec, "iters": iters, "st": st,
+            "clocks": clocks.summary()}
 
-    # ---- residual check of the result (property at full size): ||A v - lambda v|| <= tol
-    r0, r1 = solver.rows()
-    if distributed:
+
+def residual_check(cx, w, ev, vec):
+    """max_j ||A v_j - lambda_j B v_j|| of the returned eigenpairs, with the library's own block matvec on the
+    resident matrices (property at full size)."""
+    from fortran_davidson_b200.dist import partition_rows
+    np, torch, dist, s = cx.np, cx.torch, cx.dist, cx.solver
+    r0, r1 = s.rows()
+    n, L = w.n, w.lowest
+    if cx.distributed:
         # the timed solves return the Ritz vectors row-sharded (dav_solve_local); assemble them for the check
-        nl_max = max_over_ranks(float(r1 - r0))
+        nl_max = cx.max_over_ranks(float(r1 - r0))
         mine = torch.zeros((int(nl_max), L), dtype=torch.float64, device="cuda")
         mine[:r1 - r0] = torch.from_numpy(np.ascontiguousarray(vec[:r1 - r0]))
-        parts = [torch.zeros_like(mine) for _ in range(world)]
+        parts = [torch.zeros_like(mine) for _ in range(cx.world)]
         dist.all_gather(parts, mine)
-        vec = np.asfortranarray(torch.cat(parts, 0)[:n].cpu().numpy())
-    av = solver.block_matvec(0, vec)
-    bv = solver.block_matvec(1, vec) if (args.gev and not args.free) else vec[r0:r1]
-    res2 = ((av - bv * ev) ** 2).sum(axis=0)
-    if distributed:
-        t = torch.tensor(res2, dtype=torch.float64, device="cuda")
-        dist.all_reduce(t)
-        res2 = t.cpu().numpy()
-    max_res = float(np.sqrt(res2).max())
+        # rank r owns rows [r*chunk, ...): strip each part to its true row count
+        rows = []
+        for r in range(cx.world):
+            b, e = partition_rows(n, cx.world, r)
+            rows.append(parts[r][:e - b])
+        vec = np.asfortranarray(torch.cat(rows, 0).cpu().numpy())
+    av = s.block_matvec(0, vec)
+    bv = s.block_matvec(1, vec) if (w.gev and not w.free) else vec[r0:r1]
+    res2 = cx.sum_over_ranks(((av - bv * ev) ** 2).sum(axis=0))
+    return float(np.sqrt(res2).max()), vec
 
-    # ---- roofline of the dominant kernel (the block matvec): per-width timings with events on the solver stream
-    hbm_peak, hbm_src = measured_peaks()
-    nl = r1 - r0
+
+def matvec_per_width(cx, w, st, reps):
+    """Block-matvec launches of the widths the solve used (+ b = 16), alone on the resident operator, events on the
+    solver stream, median of `reps`, max over ranks."""
+    np, s = cx.np, cx.solver
+    hbm_peak, _ = measured_peaks()
+    r0, r1 = s.rows()
+    nl, n = r1 - r0, w.n
     widths = sorted(set([16] + [int(k) for k in st.trace_k[:max(st.trace_len - 1, 1)]]))
     per_width = {}
     for b in widths:
-        ms = solver.bench_block_matvec(0, b, 2 if args.free else 5)
-        ms_b = max_over_ranks(float(np.median(ms)))
+        ms = s.bench_block_matvec(0, b, reps)
+        ms_b = cx.max_over_ranks(float(np.median(ms)))
         byts = 8.0 * nl * n + 8.0 * n * b + 8.0 * nl * b
-        per_width[str(b)] = {"ms": ms_b, "GBps": byts / ms_b * 1e-6, "TFLOPs": 2.0 * nl * n * b / ms_b * 1e-9,
-                             "hbm_frac": byts / ms_b * 1e-6 / hbm_peak}
-    # FP64 peak: not in MEASURED_PEAKS.json -> measured live (cuBLAS DGEMM through torch; denominator only)
+        per_width[str(b)] = {"ms": ms_b, "TFLOPs": 2.0 * nl * n * b / ms_b * 1e-9}
+        if w.free:
+            per_width[str(b)]["Gentries_per_s"] = 1e-6 * nl * n / ms_b
+        else:
+            per_width[str(b)].update({"GBps": byts / ms_b * 1e-6, "hbm_frac": byts / ms_b * 1e-6 / hbm_peak})
+    return per_width
+
+
+def fp64_peaks(cx):
+    """FP64 peak: not in MEASURED_PEAKS.json -> measured live: cuBLAS DGEMM through torch (denominator only) and the
+    DMMA issue rate of the chip from registers (csrc/microbench.cu)."""
+    torch = cx.torch
     a = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
     bb = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
     torch.matmul(a, bb)
@@ -322,16 +405,126 @@ def main():
     p64_cublas = 2.0 * 8192 ** 3 / best * 1e-9
     del a, bb
     torch.cuda.empty_cache()
-    # ... and the DMMA issue rate of the chip from registers (csrc/microbench.cu): what the FP64 tensor pipe can do
-    # with no memory system at all.  The roofline denominator is the larger of the two.
     try:
-        p64_pipe = float(solver.bench_fp64_pipe(3))
+        p64_pipe = float(cx.solver.bench_fp64_pipe(3))
     except Exception:
         p64_pipe = 0.0
+    return p64_cublas, p64_pipe
+
+
+def phase_ms(st):
+    return {"matvec": st.matvec_ms, "rayleigh_ritz": st.rr_ms, "orthonormalise": st.orth_ms,
+            "residual_dpr": st.resid_ms, "projection": st.proj_ms, "init": st.init_ms,
+            "gather_new_block": st.gather_ms, "output_vectors": st.output_ms, "exchange_inside_phases": st.comm_ms}
+
+
+def golden_parity(cx, w, res, max_res, vec_full):
+    """The headline workload against the committed full-size oracle run: iteration count, basis schedule,
+    eigenvalues 1e-10 relative, eigenvector fingerprints up to sign 1e-8, residual <= tol."""
+    np = cx.np
+    g = golden_full_size()
+    if g is None:
+        return {"pass": False, "error": "tests/golden/config2_n100k_oracle.json missing"}
+    ev = np.asarray(res["ev"])
+    gev_ = np.asarray(g["eigenvalues"])
+    ev_rel = float(np.abs(ev - gev_).max() / np.abs(gev_).max())
+    st = res["st"]
+    trace = [int(k) for k in st.trace_k[:st.trace_len]]
+    vec_err = 0.0
+    probes = g["probe_rows"]
+    for j, fp in enumerate(g["eigenvectors"]):
+        v = vec_full[:, j]
+        v = v * (1.0 if v[fp["imax"]] >= 0 else -1.0)
+        vec_err = max(vec_err, float(np.abs(v[probes] - np.asarray(fp["probes"])).max()),
+                      abs(float(v[fp["imax"]]) - fp["vmax"]), abs(float(np.linalg.norm(v)) - fp["norm"]))
+    ok = (res["iters"] == g["iters"] and trace == g["trace_k"] and ev_rel < 1e-10 and vec_err < 1e-8
+          and max_res <= w.tol)
+    return {"pass": bool(ok), "against": "tests/golden/config2_n100k_oracle.json (oracle at full size, n=100000)",
+            "iterations": int(res["iters"]), "iterations_oracle": int(g["iters"]), "basis_schedule": trace,
+            "eigenvalues_max_rel_err": ev_rel, "eigenvector_probe_max_abs_err": vec_err, "max_residual": max_res,
+            "tolerance": w.tol, "n_gpus": cx.world}
+
+
+class W:  # one workload
+    def __init__(self, **kw):
+        self.__dict__.update(dict(n=100000, lowest=16, method="DPR", max_dim=0, sparsity=1e-4, tol=1e-8, gev=False,
+                                  free=False, gpus=1))
+        self.__dict__.update(kw)
+
+
+def run_other_config(cx, name, w, steps, warmup, golden=None, want_roofline=True):
+    """One of the other BASELINE.json configs on the current N: time, iterations, residual, per-width matvec."""
+    np = cx.np
+    out = {"workload": workload_config(w, cx.world)["workload"], "steps": steps, "warmup": warmup}
+    try:
+        gen_s = load_workload(cx, w)
+        res = timed_solves(cx, w, steps, warmup)
+        max_res, _ = residual_check(cx, w, res["ev"], res["vec"])
+        st = res["st"]
+        trace = [int(k) for k in st.trace_k[:st.trace_len]]
+        out.update({"value": res["ms_per_step"] * 1e-3, "unit": UNIT, "ms_per_step": res["ms_per_step"],
+                    "iterations": int(res["iters"]) if res["iters"] is not None else None,
+                    "iterations_per_s": (int(res["iters"]) / (res["ms_per_step"] * 1e-3)) if res["iters"] else None,
+                    "basis_schedule": trace[:8] + (["..."] if len(trace) > 8 else []),
+                    "collapses": sum(1 for i in range(1, len(trace)) if trace[i] < trace[i - 1]),
+                    "max_residual": max_res, "eigenvalues_head": [float(x) for x in res["ev"][:4]],
+                    "gpu_launches": res["launches"], "matvec_ms": res["matvec_ms"], "phase_ms": phase_ms(st),
+                    "gjd_inner_iterations": int(st.gjd_inner_iterations), "generate_s": gen_s,
+                    "collectives_per_solve": int(st.collectives)})
+        ok = max_res <= max(w.tol, 1e-8) and res["iters"] is not None
+        par = {"max_residual": max_res, "tolerance": w.tol}
+        if golden is not None:
+            gv = np.asarray(golden["eigenvalues"])
+            rel = float(np.abs(np.asarray(res["ev"]) - gv).max() / np.abs(gv).max())
+            par.update({"iterations_oracle": int(golden["iters"]), "eigenvalues_max_rel_err": rel,
+                        "against": "tests/golden/longrun_n20k_oracle.json"})
+            ok = ok and abs(int(res["iters"]) - int(golden["iters"])) <= 1 and rel < 1e-10
+        par["pass"] = bool(ok)
+        out["parity_check"] = par
+        if want_roofline:
+            pw = matvec_per_width(cx, w, st, 2 if w.free else 3)
+            out["matvec_per_width"] = pw
+    except Exception as ex:  # report, never fake
+        out["error"] = repr(ex)[:300]
+        out["parity_check"] = {"pass": False, "error": repr(ex)[:200]}
+    return out
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    cx = Ctx(args)
+    np, solver, rank, distributed = cx.np, cx.solver, cx.rank, cx.distributed
+    n, L = args.n, args.lowest
+
+    gen_s = load_workload(cx, args)
+    res = timed_solves(cx, args, args.steps, args.warmup)
+    st = res["st"]
+    ms_per_step = res["ms_per_step"]
+    value = ms_per_step * 1e-3
+    ev, iters = res["ev"], res["iters"]
+
+    # ---- parity of the timed result, outside the timed region: residual at full size + the committed oracle run
+    max_res, vec_full = residual_check(cx, args, ev, res["vec"])
+    if is_headline(args):
+        parity = golden_parity(cx, args, res, max_res, vec_full)
+    else:
+        parity = {"pass": bool(max_res <= max(args.tol, 1e-8) and iters is not None), "max_residual": max_res,
+                  "tolerance": args.tol, "against": "residual property only (no committed oracle run of this shape)"}
+    del vec_full
+
+    # ---- roofline of the dominant kernel (the block matvec): per-width timings with events on the solver stream
+    hbm_peak, hbm_src = measured_peaks()
+    r0, r1 = solver.rows()
+    nl = r1 - r0
+    per_width = matvec_per_width(cx, args, st, 2 if args.free else 5)
+    p64_cublas, p64_pipe = fp64_peaks(cx)
     p64 = max(p64_cublas, p64_pipe)
     dom_b = int(st.last_matvec_b)
-    dom = per_width.get(str(dom_b), per_width[str(widths[-1])])
-    in_solve_ms = max_over_ranks(sum(mv_ms) / len(mv_ms))
+    dom = per_width.get(str(dom_b), per_width[max(per_width, key=int)])
+    in_solve_ms = res["matvec_ms"]
     roofline = {"bound": "tensor", "achieved": dom["TFLOPs"], "peak": p64, "unit": "TFLOP/s",
                 "frac": dom["TFLOPs"] / p64, "traffic": None,
                 "kernel": "matvec_kernel (TMA + mbarrier + FP64 DMMA, 32-column stages; full waves + stream-K remainder for b > 32, stream-K below), widest block of the solve b=%d: "
@@ -341,20 +534,17 @@ def main():
                                "(dav_bench_fp64_pipe), cuBLAS DGEMM 8192^3 through torch.matmul %.2f TFLOP/s"
                                % (p64_pipe, p64_cublas),
                 "peak_cublas_dgemm": p64_cublas, "peak_dmma_pipe": p64_pipe,
-                "hbm_view": {"b": 16, "achieved": per_width["16"]["GBps"], "peak": hbm_peak, "unit": "GB/s",
-                             "frac": per_width["16"]["hbm_frac"], "peak_source": hbm_src,
-                             "note": "narrow block (HBM-bound regime): algorithmic bytes 8*nl*n + 8*n*b + 8*nl*b"},
                 "per_width": per_width, "matvec_ms_in_solve": in_solve_ms,
                 "matvec_share_of_step": in_solve_ms / ms_per_step}
-
     if args.free:
-        for v in per_width.values():
-            v["Gentries_per_s"] = 1e-6 * nl * n / v["ms"]
-            v.pop("GBps", None); v.pop("hbm_frac", None)
         roofline["hbm_view"] = None
         roofline["kernel"] = ("free_dmma_kernel (operator entries generated into swizzled shared memory by a piecewise "
                               "polynomial, FP64 DMMA against the packed X tile), widest block b=%d: 2*nl*n*b flops / launch; "
                               "bound = FP64 pipe shared by DMMA and the generator" % dom_b)
+    else:
+        roofline["hbm_view"] = {"b": 16, "achieved": per_width["16"]["GBps"], "peak": hbm_peak, "unit": "GB/s",
+                                "frac": per_width["16"]["hbm_frac"], "peak_source": hbm_src,
+                                "note": "narrow block (HBM-bound regime): algorithmic bytes 8*nl*n + 8*n*b + 8*nl*b"}
     traffic = measured_traffic(args, dom_b)
     if traffic is not None:
         roofline["traffic"] = traffic["bytes"]
@@ -364,18 +554,16 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, args.gpus),
             "iterations": int(iters) if iters is not None else None,
+            "iterations_per_s": (int(iters) / value) if iters else None,
             "basis_schedule": [int(k) for k in st.trace_k[:st.trace_len]],
-            "eigenvalues_head": [float(x) for x in ev[:4]], "max_residual": max_res,
-            "wall_ms_per_step": wall_ms, "generate_s": gen_s,
-            "phase_ms": {"matvec": st.matvec_ms, "rayleigh_ritz": st.rr_ms, "orthonormalise": st.orth_ms,
-                         "residual_dpr": st.resid_ms, "projection": st.proj_ms, "init": st.init_ms,
-                         "gather_new_block": st.gather_ms, "output_vectors": st.output_ms,
-                         "nccl_inside_phases": st.comm_ms},
+            "eigenvalues_head": [float(x) for x in ev[:4]], "max_residual": max_res, "parity_check": parity,
+            "wall_ms_per_step": res["wall_ms"], "generate_s": gen_s,
+            "phase_ms": phase_ms(st), "spans_dropped": int(st.spans_dropped),
             "collectives_per_solve": int(st.collectives),
             "transport": (("peer-memory kernels (cudaIpc-mapped NVLink stores, csrc/comm.cu)" if solver.comm_info()["peer"]
                            else "NCCL") if distributed else "single GPU"),
-            "gpu_launches": int(sum(launches) / len(launches)), "matvec_launches": int(mv_launch[-1]),
-            "clocks": clocks.summary(), "roofline": roofline}
+            "gpu_launches": res["launches"], "matvec_launches": res["matvec_launches"],
+            "clocks": res["clocks"], "roofline": roofline}
 
     # ---- end to end through the drop-in C ABI with HOST buffers (upload inside the timed region)
     e2e = None
@@ -383,22 +571,50 @@ def main():
         e2e = {"value": None, "unit": UNIT, "skipped": "e2e is measured on the default workload only"}
     elif not args.no_e2e:
         try:
-            e2e = run_e2e(args, solver, fd, torch, dist, distributed, rank, world, n, L, md, barrier, max_over_ranks)
+            e2e = run_e2e(args, solver, cx.fd, cx.torch, cx.dist, distributed, rank, cx.world, n, L, args.max_dim or None,
+                          cx.barrier, cx.max_over_ranks)
         except Exception as ex:  # report, never fake
             e2e = {"value": None, "unit": UNIT, "error": repr(ex)[:300]}
     line["e2e"] = e2e if e2e is not None else {"value": None, "unit": UNIT, "skipped": "--no-e2e"}
 
-    # ---- CPU baseline on the box's host cores (rank 0, N=1 only)
+    # ---- the other BASELINE.json configs on this N (attached, not the headline), each to the same parity bar
+    if is_headline(args) and not args.no_other:
+        other = {}
+        k_s, k_w = min(args.steps, 5), min(max(args.warmup, 1), 3)
+        other["configs[1]"] = run_other_config(cx, "configs[1]", W(n=20000, lowest=10, max_dim=100), k_s, k_w)
+        other["configs[3]"] = run_other_config(cx, "configs[3]", W(n=50000, lowest=8, method="GJD", gev=True), k_s, k_w)
+        glong = os.path.join(ROOT, "tests", "golden", "longrun_n20k_oracle.json")
+        other["long_run"] = run_other_config(
+            cx, "long_run", W(n=20000, lowest=10, max_dim=30, sparsity=5e-2), k_s, k_w,
+            golden=json.load(open(glong)) if os.path.exists(glong) else None, want_roofline=False)
+        if args.gpus >= 8 or args.with_free:
+            other["configs[4]"] = run_other_config(cx, "configs[4]", W(n=2000000, lowest=32, free=True, gev=True), 2, 1)
+        line["other_configs"] = other
+
+    # ---- CPU baseline on the box's host cores (rank 0, N=1 only): bounded sample; the full-size measurement is the
+    # `--impl reference` arm and the committed golden run
     if rank == 0 and args.gpus == 1 and not args.no_cpu and not (args.free or args.gev or args.method != "DPR"):
         try:
-            line["cpu_baseline"] = cpu_reference_run(args, 1, 0, budget_s=25.0)
+            cb = cpu_reference_run(args, 25.0, full_size=False)
+            g = golden_full_size() if is_headline(args) else None
+            if g is not None:
+                cb["full_size_measured"] = {"seconds": g["host"]["solve_s"], "cores": g["host"]["cores"],
+                                            "source": "tests/golden/config2_n100k_oracle.json (one oracle solve at "
+                                                      "n=100000 on a GPU box host; re-measured by --impl reference)"}
+            line["cpu_baseline"] = cb
         except Exception as ex:
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "error": repr(ex)[:300]}
     solver.close()
+    fails = [k for k, v in line.get("other_configs", {}).items() if not v.get("parity_check", {}).get("pass", False)]
+    ok = bool(parity.get("pass")) and not fails
+    line["parity_ok"] = ok
     if rank == 0:
         print(json.dumps(line))
     if distributed:
-        dist.destroy_process_group()
+        cx.dist.destroy_process_group()
+    if not ok:
+        sys.stderr.write("bench.py: PARITY CHECK FAILED: %s %s\n" % (json.dumps(parity), fails))
+        sys.exit(1)
 
 
 def run_e2e(args, solver, fd, torch, dist, distributed, rank, world, n, L, md, barrier, max_over_ranks):

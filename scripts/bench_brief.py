@@ -14,4 +14,8 @@ for path in sys.argv[1:]:
                       "iterations": d.get("iterations"), "max_residual": d.get("max_residual"), "phase_ms": ph,
                       "collectives": d.get("collectives_per_solve"), "launches": d.get("gpu_launches"),
                       "transport": d.get("transport"), "parity": d.get("parity_check"),
-                      "e2e": (d.get("e2e") or {}).get("value")}))
+                      "e2e": (d.get("e2e") or {}).get("value"),
+                      "other": {k: {"ms": round(v.get("ms_per_step") or 0, 3), "iters": v.get("iterations"),
+                                    "it/s": round(v.get("iterations_per_s") or 0, 1),
+                                    "ok": (v.get("parity_check") or {}).get("pass"), "err": v.get("error")}
+                                for k, v in (d.get("other_configs") or {}).items()}}))
