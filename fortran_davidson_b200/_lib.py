@@ -25,7 +25,7 @@ SYMBOLS = [
     "dav_lapack_generalized_eigensolver_lowest", "dav_sym_eigh_info", "dav_lapack_qr", "dav_lapack_solver", "dav_lapack_matmul",
     "dav_lapack_matrix_vector", "dav_lapack_sort", "dav_free_matmul", "dav_compute_on_the_fly",
     "dav_debug_matvec_schedule", "dav_bench_fp64_pipe", "dav_debug_matvec_rect", "dav_debug_collective",
-    "dav_comm_info", "dav_debug_chol_inv",
+    "dav_comm_info", "dav_debug_chol_inv", "dav_debug_gemm_bench",
 ]
 
 

@@ -404,6 +404,56 @@ int dav_debug_chol_inv(int b, const double* g, double* t, double* flag, float* m
   API_END
 }
 
+int dav_debug_gemm_bench(char transA, int64_t m, int64_t n, int64_t k, int reps, int to_partials, float* ms_out,
+                         double* max_err) {
+  API_BEGIN
+  need((transA == 'N' || transA == 'T') && m >= 1 && n >= 1 && k >= 1 && reps >= 1 && ms_out, "bad arguments");
+  Ctx c;
+  const bool ta = transA == 'T';
+  // operands as the solver has them: tall blocks with a padded leading dimension, small factors dense
+  const int64_t lda = ta ? round_up(k, 16) : round_up(m, 16), ldb = ta ? round_up(k, 16) : k;
+  DevBuf<double> A, B, Cm, Cr, ws;
+  A.alloc((size_t)lda * (ta ? m : k));
+  B.alloc((size_t)ldb * n);
+  Cm.alloc((size_t)m * n);
+  Cr.alloc((size_t)m * n);
+  ws.alloc(std::max<size_t>((size_t)m * n * 600, (size_t)1 << 22));
+  fill_random(c.s, A.p, A.n, 11);
+  fill_random(c.s, B.p, B.n, 12);
+  int parts = 0;
+  auto run = [&]() {
+    if (to_partials && ta) gemm(c.s, ta, m, n, k, 1.0, A.p, lda, B.p, ldb, 0.0, nullptr, 0, ws.p, ws.n, &parts);
+    else gemm(c.s, ta, m, n, k, 1.0, A.p, lda, B.p, ldb, 0.0, Cm.p, m, ws.p, ws.n);
+  };
+  run();
+  std::vector<cudaEvent_t> ev(2 * (size_t)reps);
+  for (auto& e : ev) CK(cudaEventCreate(&e));
+  for (int r = 0; r < reps; ++r) {
+    CK(cudaEventRecord(ev[2 * r], c.s));
+    run();
+    CK(cudaEventRecord(ev[2 * r + 1], c.s));
+  }
+  c.sync();
+  for (int r = 0; r < reps; ++r) CK(cudaEventElapsedTime(&ms_out[r], ev[2 * r], ev[2 * r + 1]));
+  for (auto& e : ev) cudaEventDestroy(e);
+  if (max_err) {  // against the SIMT kernel (the in-library reference), only for the direct (non-partial) form
+    *max_err = -1.0;
+    if (!(to_partials && ta)) {
+      setenv("DAV_GEMM_IMPL", "0", 1);
+      gemm(c.s, ta, m, n, k, 1.0, A.p, lda, B.p, ldb, 0.0, Cr.p, m, ws.p, ws.n);
+      unsetenv("DAV_GEMM_IMPL");
+      std::vector<double> h1((size_t)m * n), h2((size_t)m * n);
+      d2h(h1.data(), Cm.p, h1.size(), c.s);
+      d2h(h2.data(), Cr.p, h2.size(), c.s);
+      c.sync();
+      double e = 0.0;
+      for (size_t i = 0; i < h1.size(); ++i) e = std::max(e, std::fabs(h1[i] - h2[i]));
+      *max_err = e;
+    }
+  }
+  API_END
+}
+
 int dav_comm_info(dav_solver_t* h, int* peer_transport, long long* peer_calls, long long* nccl_calls) {
   API_BEGIN
   need(h, "bad handle");

@@ -127,20 +127,39 @@ __global__ void __launch_bounds__(NT) gemm_kernel(int64_t M, int64_t N, int64_t 
 
 // Tensor-pipe variant.  Fragment layout of mma.sync.m8n8k4.f64 (g = lane >> 2, t = lane & 3): a = op(A)[m0+g][k+t],
 // b = B[k+t][n0+g], d0/d1 = C[m0+g][n0+2t], C[m0+g][n0+2t+1].  TA: A is stored K x M (the projections, K = local rows).
-template <bool TA>
-__global__ void __launch_bounds__(128) gemm_dmma_kernel(int64_t M, int64_t N, int64_t K, int64_t Kchunk, double alpha,
-                                                        const double* __restrict__ A, int64_t lda,
-                                                        const double* __restrict__ B, int64_t ldb, double beta,
-                                                        double* __restrict__ C, int64_t ldc, double* __restrict__ ws,
-                                                        int splits, int to_ws) {
+//
+// r02: these products are latency-bound, not flop-bound, whenever a rank holds few rows (8 GPUs: 12,500): the r01
+// kernel walked K with at most two k-steps of loads in flight per warp and 4 warps per CTA -- 40 us for a 50 MFLOP
+// projection.  Now (i) the k-loop is processed in chunks of UN = 4 k-steps whose 32 loads per lane are all issued
+// before the 64 DMMAs that consume them, (ii) KG warp groups per CTA take interleaved quarters of the CTA's K range
+// and are summed through shared memory in a fixed tree order (bit-reproducible) -- the dependent chain per warp is
+// KG times shorter and the number of split-K partials does not grow, (iii) blocks of <= 32 columns use a 128 x 32
+// CTA tile (WNS = 1) so that no warp idles on columns that do not exist.  Out-of-range rows / columns of a sub-tile
+// read clamped (valid) addresses and accumulate into registers that are never stored.
+constexpr int UN_MAX = 4;
+
+template <bool TA, int KG, int WNS, bool VEC>
+__global__ void __launch_bounds__(128 * KG) gemm_dmma_kernel(int64_t M, int64_t N, int64_t K, int64_t Kchunk,
+                                                             double alpha, const double* __restrict__ A, int64_t lda,
+                                                             const double* __restrict__ B, int64_t ldb, double beta,
+                                                             double* __restrict__ C, int64_t ldc,
+                                                             double* __restrict__ ws, int splits, int to_ws) {
+  extern __shared__ __align__(16) double red_sm[];
+  constexpr int WMS = 4 / WNS;
+  constexpr int UN = KG == 4 ? 2 : UN_MAX;  // 512 threads leave 128 registers per thread: two k-steps in flight
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int64_t m0 = (int64_t)blockIdx.x * BM + (warp & 1) * 32;
-  const int64_t n0 = (int64_t)blockIdx.y * BN + (warp >> 1) * 32;
-  if (m0 >= M || n0 >= N) return;  // warp-uniform: the whole warp leaves together
+  const int sub = warp & 3, kg = warp >> 2;
+  const int64_t m0 = (int64_t)blockIdx.x * (32 * WMS) + (sub % WMS) * 32;
+  const int64_t n0 = (int64_t)blockIdx.y * (32 * WNS) + (sub / WMS) * 32;
+  const bool active = m0 < M && n0 < N;  // warp-uniform
   const int z = blockIdx.z;
   const int64_t kbeg = (int64_t)z * Kchunk;
   const int64_t kend = min(K, kbeg + Kchunk);
+  // this warp group's part of [kbeg, kend): contiguous, a multiple of 4 rows
+  const int64_t per = ((kend - kbeg + KG - 1) / KG + 3) & ~(int64_t)3;
+  const int64_t gb = kbeg + (int64_t)kg * per;
+  const int64_t ge = min(kend, gb + per);
 
   double acc[4][4][2];
 #pragma unroll
@@ -148,38 +167,132 @@ __global__ void __launch_bounds__(128) gemm_dmma_kernel(int64_t M, int64_t N, in
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  // per-lane base pointers and bounds of the four m-tiles / n-tiles
-  const double* ap[4];
-  const double* bp[4];
-  bool am[4], bn[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int64_t m = m0 + 8 * i + g;
-    am[i] = m < M;
-    ap[i] = TA ? A + (am[i] ? m : 0) * lda + t : A + (am[i] ? m : 0) + (int64_t)t * lda;
-    const int64_t n = n0 + 8 * i + g;
-    bn[i] = n < N;
-    bp[i] = B + (bn[i] ? n : 0) * ldb + t;
-  }
-  const int64_t astep = TA ? 1 : lda;  // distance between consecutive k in op(A)
-
-#pragma unroll 2
-  for (int64_t kk = kbeg; kk < kend; kk += 4) {
-    const bool kin = kk + t < kend;
-    double a[4], b[4];
+  if (active && gb < ge) {
+    // per-lane base pointers (clamped to a valid row / column) of the four m-tiles / n-tiles
+    const double* ap[4];
+    const double* bp[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      a[i] = (kin && am[i]) ? ap[i][kk * astep] : 0.0;
-      b[i] = (kin && bn[i]) ? bp[i][kk] : 0.0;
+      const int64_t m = min(m0 + 8 * i + g, M - 1);
+      ap[i] = TA ? A + m * lda + t : A + m + (int64_t)t * lda;
+      const int64_t n = min(n0 + 8 * i + g, N - 1);
+      bp[i] = B + n * ldb + t;
     }
+    const int64_t astep = TA ? 1 : lda;  // distance between consecutive k in op(A)
+    // which 8-wide tiles of this warp exist at all (warp-uniform): skipped MMAs for N = 16, edge tiles
+    bool mi[4], nj[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 4; ++i) {
+      mi[i] = m0 + 8 * i < M;
+      nj[i] = n0 + 8 * i < N;
+    }
+    int64_t kk = gb;
+    if (VEC) {
+      // TN, 16-byte aligned operands: the order of the k index inside an MMA is free as long as A and B agree, so
+      // lane t takes 2 VH CONSECUTIVE rows of its column with VH 16-byte loads and feeds one of them to each of the
+      // chunk's 2 VH MMAs -- half as many load instructions (and L1 wavefronts) per flop
+      constexpr int VH = KG == 4 ? 1 : 2;  // 16-byte loads per tile and chunk (512 threads: 128 registers each)
+      for (; kk + 8 * VH <= ge; kk += 8 * VH) {
+        double2 a[4][VH], b[4][VH];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-            : "+d"(acc[i][j][0]), "+d"(acc[i][j][1])
-            : "d"(a[i]), "d"(b[j]));
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int h = 0; h < VH; ++h) {
+            // rows kk + 2 VH t + 2h, +1 (ap / bp carry + t already)
+            a[i][h] = *reinterpret_cast<const double2*>(ap[i] + kk + (2 * VH - 1) * t + 2 * h);
+            b[i][h] = *reinterpret_cast<const double2*>(bp[i] + kk + (2 * VH - 1) * t + 2 * h);
+          }
+#pragma unroll
+        for (int u = 0; u < 2 * VH; ++u)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (!mi[i]) continue;
+            const double av = (u & 1) ? a[i][u >> 1].y : a[i][u >> 1].x;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (!nj[j]) continue;
+              const double bv = (u & 1) ? b[j][u >> 1].y : b[j][u >> 1].x;
+              asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                  : "+d"(acc[i][j][0]), "+d"(acc[i][j][1])
+                  : "d"(av), "d"(bv));
+            }
+          }
+      }
+    }
+    for (; kk + 4 * UN <= ge; kk += 4 * UN) {
+      double a[UN][4], b[UN][4];
+#pragma unroll
+      for (int u = 0; u < UN; ++u)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          a[u][i] = ap[i][(kk + 4 * u) * astep];
+          b[u][i] = bp[i][kk + 4 * u];
+        }
+#pragma unroll
+      for (int u = 0; u < UN; ++u)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (!mi[i]) continue;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (!nj[j]) continue;
+            asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                : "+d"(acc[i][j][0]), "+d"(acc[i][j][1])
+                : "d"(a[u][i]), "d"(b[u][j]));
+          }
+        }
+    }
+    for (; kk < ge; kk += 4) {  // tail: fewer than 4 UN rows left, the last k-step may be partial
+      const bool kin = kk + t < ge;
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        a[i] = kin ? ap[i][kk * astep] : 0.0;
+        b[i] = kin ? bp[i][kk] : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (!mi[i]) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (!nj[j]) continue;
+          asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+              : "+d"(acc[i][j][0]), "+d"(acc[i][j][1])
+              : "d"(a[i]), "d"(b[j]));
+        }
+      }
+    }
   }
+
+  // sum of the KG warp groups, fixed tree order: (g0 + g2) + (g1 + g3) for KG = 4, g0 + g1 for KG = 2
+  if (KG > 1) {
+#pragma unroll
+    for (int half = KG / 2; half >= 1; half >>= 1) {
+      if (kg >= half && kg < 2 * half) {
+        double* slot = red_sm + ((size_t)((kg - half) * 4 + sub) * 32) * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            slot[((i * 4 + j) * 2) * 32] = acc[i][j][0];
+            slot[((i * 4 + j) * 2 + 1) * 32] = acc[i][j][1];
+          }
+      }
+      __syncthreads();
+      if (kg < half) {
+        const double* slot = red_sm + ((size_t)(kg * 4 + sub) * 32) * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[i][j][0] += slot[((i * 4 + j) * 2) * 32];
+            acc[i][j][1] += slot[((i * 4 + j) * 2 + 1) * 32];
+          }
+      }
+      if (half > 1) __syncthreads();
+    }
+  }
+  if (kg != 0 || !active) return;
 
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -226,6 +339,22 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(int64_t M, int64_t N
 
 }  // namespace
 
+namespace {
+template <bool TA, int KG, int WNS, bool VEC>
+void launch_dmma(cudaStream_t s, dim3 grid, int64_t M, int64_t N, int64_t K, int64_t Kchunk, double alpha,
+                 const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
+                 double* ws, int splits, int to_ws) {
+  const size_t sm = KG > 1 ? (size_t)(KG / 2) * 4 * 32 * 32 * sizeof(double) : 0;
+  if (sm > 48 * 1024) ensure_dyn_smem(gemm_dmma_kernel<TA, KG, WNS, VEC>, (int)sm);
+  gemm_dmma_kernel<TA, KG, WNS, VEC><<<grid, 128 * KG, sm, s>>>(M, N, K, Kchunk, alpha, A, lda, B, ldb, beta, C, ldc, ws,
+                                                          splits, to_ws);
+}
+int env_or(const char* name, int dflt) {
+  const char* e = std::getenv(name);
+  return e ? std::atoi(e) : dflt;
+}
+}  // namespace
+
 void gemm(cudaStream_t s, bool transA, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
           const double* B, int64_t ldb, double beta, double* C, int64_t ldc, double* ws, size_t ws_doubles,
           int* partials_out) {
@@ -237,16 +366,24 @@ void gemm(cudaStream_t s, bool transA, int64_t M, int64_t N, int64_t K, double a
     DAV_THROW(DAV_ERR_STATE, "gemm: workspace too small for the partials of a %lld x %lld product", (long long)M,
               (long long)N);
   const int to_ws = partials_out ? 1 : 0;
-  const int64_t gx = ceil_div(M, BM), gy = ceil_div(N, BN);
+  // read per call so one process can compare the implementations (tests, bench A/B)
+  const int impl = env_or("DAV_GEMM_IMPL", GEMM_IMPL_DEFAULT);
+  // tensor-pipe kernel: 128 x 32 CTA tiles for blocks of <= 32 columns, 64 x 64 otherwise
+  const int wns = (impl == 1 && N <= 32) ? 1 : 2;
+  const int bm = impl == 1 ? 32 * (4 / wns) : BM, bn = impl == 1 ? 32 * wns : BN;
+  const int64_t gx = ceil_div(M, bm), gy = ceil_div(N, bn);
+  // warp groups per CTA along K (tensor-pipe kernel): 4 whenever every group still gets a full chunk of UN k-steps
+  int kg = env_or("DAV_GEMM_KG", 0);
+  if (kg != 1 && kg != 2 && kg != 4) kg = 0;
   int splits = 1;
-  // read per call so one process can compare the two implementations (tests, bench A/B)
-  const char* impl_env = std::getenv("DAV_GEMM_IMPL");
-  const int impl = impl_env ? std::atoi(impl_env) : GEMM_IMPL_DEFAULT;
   if (K > 1024 && gx * gy < 592) {  // long reduction, few output tiles: split K over the grid
-    // about two CTAs per SM in total: more partials only lengthen the reduction (each is M x N doubles of traffic)
-    const char* tgt_env = std::getenv("DAV_GEMM_SPLIT_TARGET");
-    const int64_t target = tgt_env ? std::max(1, std::atoi(tgt_env)) : GEMM_SPLIT_TARGET_DEFAULT;
-    splits = (int)std::min<int64_t>(ceil_div(target, gx * gy), ceil_div(K, 256));
+    // about one CTA (8-16 warps) per SM in total: more partials only lengthen the reduction (each is M x N doubles)
+    const int64_t target = std::max(1, env_or("DAV_GEMM_SPLIT_TARGET", GEMM_SPLIT_TARGET_DEFAULT));
+    // rows of K a CTA should at least own (measured, r02_gemm_bench: 12,500 rows -> ~130 CTAs of 96 rows beat both
+    // 196 x 64 and 74 x 176; 100,000 rows -> 296 CTAs of ~340 rows beat 148 x 680 by up to 2x on wide outputs)
+    const int64_t min_rows = impl == 1 ? 96 : 256;
+    splits = (int)std::min<int64_t>(ceil_div(target, gx * gy), ceil_div(K, min_rows));
+    (void)0;
     const size_t need = (size_t)M * (size_t)N;
     if (ws == nullptr || need == 0) splits = 1;
     else splits = (int)std::min<size_t>((size_t)splits, ws_doubles / need);
@@ -256,14 +393,35 @@ void gemm(cudaStream_t s, bool transA, int64_t M, int64_t N, int64_t K, double a
   splits = (int)ceil_div(std::max<int64_t>(K, 1), Kchunk);
   if (gy > 65535 || splits > 65535) DAV_THROW(DAV_ERR_INVALID, "gemm grid too large");
   dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)splits);
-  if (impl == 1 && transA)
-    gemm_dmma_kernel<true><<<grid, 128, 0, s>>>(M, N, K, Kchunk, alpha, A, lda, B, ldb, beta, C, ldc, ws, splits, to_ws);
-  else if (impl == 1)
-    gemm_dmma_kernel<false><<<grid, 128, 0, s>>>(M, N, K, Kchunk, alpha, A, lda, B, ldb, beta, C, ldc, ws, splits, to_ws);
-  else if (transA)
+  if (impl == 1) {
+    // warp groups along K: only the long split-K chunks (>= 256 rows per CTA: one rank holding ~100,000 rows) gain
+    // from the shorter dependent chain (-8 % on wide outputs); short chunks and the NN shapes (K <= a few hundred,
+    // thousands of CTAs) are faster with 4-warp CTAs and no shared-memory sum (measured, profiles/r02_gemm_bench*)
+    if (kg == 0) kg = (transA && Kchunk >= 256) ? 4 : 1;
+    const bool vec = transA && env_or("DAV_GEMM_VEC", 1) != 0 && lda % 2 == 0 && ldb % 2 == 0 &&
+                     (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0;
+#define DAV_GEMM_CASE(TA_, KG_, WNS_, VEC_)                                                                         \
+  launch_dmma<TA_, KG_, WNS_, VEC_>(s, grid, M, N, K, Kchunk, alpha, A, lda, B, ldb, beta, C, ldc, ws, splits, to_ws)
+#define DAV_GEMM_KG(TA_, WNS_, VEC_)                                   \
+  do {                                                                 \
+    if (kg == 4) DAV_GEMM_CASE(TA_, 4, WNS_, VEC_);                    \
+    else if (kg == 2) DAV_GEMM_CASE(TA_, 2, WNS_, VEC_);               \
+    else DAV_GEMM_CASE(TA_, 1, WNS_, VEC_);                            \
+  } while (0)
+    if (transA && vec) {
+      if (wns == 1) DAV_GEMM_KG(true, 1, true); else DAV_GEMM_KG(true, 2, true);
+    } else if (transA) {
+      if (wns == 1) DAV_GEMM_KG(true, 1, false); else DAV_GEMM_KG(true, 2, false);
+    } else {
+      if (wns == 1) DAV_GEMM_KG(false, 1, false); else DAV_GEMM_KG(false, 2, false);
+    }
+#undef DAV_GEMM_KG
+#undef DAV_GEMM_CASE
+  } else if (transA) {
     gemm_kernel<true><<<grid, NT, 0, s>>>(M, N, K, Kchunk, alpha, A, lda, B, ldb, beta, C, ldc, ws, splits, to_ws);
-  else
+  } else {
     gemm_kernel<false><<<grid, NT, 0, s>>>(M, N, K, Kchunk, alpha, A, lda, B, ldb, beta, C, ldc, ws, splits, to_ws);
+  }
   CK_LAUNCH();
   ++g_kernel_launches;
   if (partials_out) {  // the caller reduces the partials itself (Comm::reduce_sum: split-K + ranks + layout)

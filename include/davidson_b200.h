@@ -200,6 +200,14 @@ int dav_debug_matvec_rect(int device, int64_t m, int64_t k, int b, double* max_a
  * below); *flag = 1.0 when a pivot was not safely positive (t is then undefined); *ms (may be NULL) = kernel time. */
 int dav_debug_chol_inv(int b, const double* g, double* t, double* flag, float* ms);
 
+/* Timing entry of the tall-skinny products around the block matvec (csrc/dgemm.cu), operands generated on the
+ * device: C (m x n) = op(A) * B with op(A) m x k, B k x n; transA 'T' = the projection shape (k = local rows, split-K).
+ * ms_out[reps] = event time of each call; to_partials != 0 (transA 'T' only): the product is left as split-K
+ * partials, as the solver's fused reduce consumes it.  *max_err (may be NULL) = max |C - C_simt| against the SIMT
+ * kernel of the same library (-1 when not compared). */
+int dav_debug_gemm_bench(char transA, int64_t m, int64_t n, int64_t k, int reps, int to_partials, float* ms_out,
+                         double* max_err);
+
 /* Self-check and timing of the inter-GPU exchanges of a distributed handle (collective: every rank calls it with the
  * same arguments).  kind 0 = all-reduce on the transport in use (peer-memory kernel when the GPUs map each other,
  * else NCCL), 1 = all-reduce through NCCL, 2 = gather of an n x count block (every rank stores its rows into every
