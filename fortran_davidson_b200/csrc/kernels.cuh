@@ -68,7 +68,7 @@ inline size_t jacobi_scratch_doubles(int k) { return 44 * (size_t)(k + 2) * (siz
 void jacobi_eigh(cudaStream_t s, int k, double* S, double* Y, double* w, double* scratch, int* status,
                  const int* skip = nullptr);
 // ---- trideig.cu : the Rayleigh-Ritz eigensolver.  Same contract as jacobi_eigh (S: upper triangle read, NOT
-// modified).  k >= 48: Householder tridiagonalisation + one warp per eigenpair (multisection, twisted
+// modified).  k >= 16: Householder tridiagonalisation + one warp per eigenpair (multisection, twisted
 // factorisation, back-transformation) + a-posteriori guard; Jacobi when the guard rejects or k is small.
 // scratch: >= sym_eigh_scratch_doubles(k).
 size_t sym_eigh_scratch_doubles(int k);

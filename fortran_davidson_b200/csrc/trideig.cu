@@ -230,6 +230,267 @@ __global__ void __launch_bounds__(1024) tridiag_kernel(int k, const double* __re
   }
 }
 
+// ---- 1b. the same tridiagonalisation with the matrix in REGISTERS (k <= 128: every Rayleigh-Ritz problem of the
+// headline solve).  The shared-memory kernel above spends ~35 issued instructions per matrix entry and step on
+// addressing, bounds and LDS/STS (17.7 k warp-instructions per step at k = 128: 2.8 us per step, 353 us in total);
+// here the full symmetric matrix lives in a 16 x 16 grid of threads, thread (ty, tx) holding the TS x TS tile of rows
+// TS ty.. and columns TS tx.. (TS = 2 / 4 / 8 for k <= 32 / 64 / 128), and a step is
+//   reflector scalars, v at my rows / columns       from the published row j (shared memory), redundantly per thread
+//   p = tau S v                                      TS^2 FMAs + a reduce-scatter over the 16 lanes of a row of tiles
+//   barrier 1
+//   K = -tau/2 (p.v)                                 16-lane all-reduce, redundantly per half warp
+//   S -= v w^T + w v^T,  w = p + K v                 2 TS^2 FMAs, registers only, tiles left of / above the front skip
+//   owners of row j+1 publish it + its tail norm     barrier 2
+// Dead rows / columns (<= j) are masked out of w, so they are never touched again; d, e, tau and the reflectors go to
+// global memory from the published row.  Rounding differs from the kernel above only in summation order.
+template <int TS>
+__device__ __forceinline__ int reduce_scatter16(double (&v)[TS], int tx) {
+  // sum over the 16 lanes of a half warp; afterwards v[0] of lane tx is the total of entry `return value`
+  int idx = 0;
+  if constexpr (TS == 8) {
+    const bool up = tx & 8;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const double send = up ? v[q] : v[q + 4];
+      const double keep = up ? v[q + 4] : v[q];
+      v[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    idx += up ? 4 : 0;
+  }
+  if constexpr (TS >= 4) {
+    constexpr int M = TS == 8 ? 4 : 8;
+    const bool up = tx & M;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const double send = up ? v[q] : v[q + 2];
+      const double keep = up ? v[q + 2] : v[q];
+      v[q] = keep + __shfl_xor_sync(0xffffffffu, send, M);
+    }
+    idx += up ? 2 : 0;
+  }
+  {
+    constexpr int M = TS == 8 ? 2 : (TS == 4 ? 4 : 8);
+    const bool up = tx & M;
+    const double send = up ? v[0] : v[1];
+    const double keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, M);
+    idx += up ? 1 : 0;
+#pragma unroll
+    for (int m2 = M >> 1; m2 >= 1; m2 >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], m2);
+  }
+  return idx;
+}
+
+__device__ __forceinline__ double allreduce16(double x) {
+#pragma unroll
+  for (int m = 8; m >= 1; m >>= 1) x += __shfl_xor_sync(0xffffffffu, x, m);
+  return x;
+}
+
+template <int TS>
+__global__ void __launch_bounds__(256) tridiag_reg_kernel(int k, const double* __restrict__ S_in,
+                                                          double* __restrict__ Sfull, double* __restrict__ Vh,
+                                                          double* __restrict__ tau, double* __restrict__ d,
+                                                          double* __restrict__ e, double* __restrict__ scal) {
+  constexpr int KP = 16 * TS;
+  __shared__ __align__(16) double rowb[KP];  // row j of the current matrix (owners only)
+  __shared__ __align__(16) double vb[KP];    // reflector j: 0 for rows <= j, 1 at row j+1
+  __shared__ __align__(16) double pb[KP];    // p = tau S v, exactly 0 on dead rows
+  __shared__ double tjb;                     // tau of reflector j
+  __shared__ double red[8];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, warp = tid >> 5;
+  // rows of a tile are contiguous (TS ty ..); its columns are the pairs 2 tx, 2 tx + 1 of every 32-column group, so
+  // that the 16 lanes of a half warp read 256 contiguous bytes of v / p with each 16-byte load (conflict-free)
+  const int r0 = ty * TS, c0 = 2 * tx;
+  auto col = [&](int q) { return c0 + 32 * (q >> 1) + (q & 1); };
+  double t[TS][TS];
+  double mx = 0.0;
+#pragma unroll
+  for (int i = 0; i < TS; ++i)
+#pragma unroll
+    for (int jj = 0; jj < TS; ++jj) {
+      const int a = r0 + i, c = col(jj);
+      double x = 0.0;
+      if (a < k && c < k) {
+        x = S_in[min(a, c) + (size_t)max(a, c) * k];  // DSYEV 'U': only the upper triangle is read
+        Sfull[a + (size_t)c * k] = x;
+        Vh[a + (size_t)c * k] = 0.0;
+      }
+      t[i][jj] = x;
+      mx = fmax(mx, fabs(x));  // NaN is dropped here and caught by the guard
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((tid & 31) == 0) red[warp] = mx;
+  for (int i = tid; i < KP; i += 256) pb[i] = 0.0;
+
+  // The warp that owns row jn builds reflector jn from it: v -> vb (and Vh), tau -> tjb (and tau[]), d, e.  The
+  // step loop keeps its code small on purpose (one SM's instruction cache serves 8 warps in lock step): the row is
+  // picked with a switch on jn % TS, and everyone else only ever loads finished vectors.
+  auto publish = [&](int jn) {
+    if ((ty >> 1) != ((jn / TS) >> 1)) return;  // warp-uniform: the shuffles below need the whole warp
+    const bool own = ty == jn / TS;
+    double x[TS];
+    switch (jn % TS) {
+#define TRI_ROW(I_)                                   \
+  case I_:                                            \
+    if constexpr (I_ < TS) {                          \
+      _Pragma("unroll") for (int jj = 0; jj < TS; ++jj) x[jj] = t[I_][jj]; \
+    }                                                 \
+    break;
+      TRI_ROW(0) TRI_ROW(1) TRI_ROW(2) TRI_ROW(3) TRI_ROW(4) TRI_ROW(5) TRI_ROW(6) TRI_ROW(7)
+#undef TRI_ROW
+      default: break;
+    }
+    double ssq = 0.0;
+#pragma unroll
+    for (int jj = 0; jj < TS; ++jj) {
+      if (own) rowb[col(jj)] = x[jj];
+      if (col(jj) > jn + 1) ssq = fma(x[jj], x[jj], ssq);
+    }
+    const double sigma = allreduce16(ssq);
+    __syncwarp();
+    const double alpha = rowb[min(jn + 1, KP - 1)];
+    double tj = 0.0, beta = alpha, scale = 0.0;
+    if (sigma > 0.0) {
+      // beta = -sign(alpha) sqrt(alpha^2 + sigma); tau = (beta - alpha) / beta = 1 + |alpha| / |beta|;
+      // scale = 1 / (alpha - beta) = sign(alpha) / (|alpha| + |beta|): one rsqrt and one reciprocal, no division
+      const double h2 = fma(alpha, alpha, sigma);
+      const double rs = rsqrt(h2);
+      const double nrm = h2 * rs;
+      beta = -copysign(nrm, alpha);
+      tj = fma(fabs(alpha), rs, 1.0);
+      scale = copysign(__drcp_rn(fabs(alpha) + nrm), alpha);
+    }
+    if (own) {
+#pragma unroll
+      for (int jj = 0; jj < TS; ++jj) {
+        const int c = col(jj);
+        const double v = c == jn + 1 ? 1.0 : ((c > jn + 1 && tj != 0.0) ? x[jj] * scale : 0.0);
+        vb[c] = v;
+        if (c < k && jn + 2 < k) Vh[(size_t)jn * k + c] = v;
+      }
+      if (tx == 0 && jn + 2 < k) {
+        tjb = tj;
+        tau[jn] = tj;
+        d[jn] = rowb[jn];
+        e[jn] = beta;
+      }
+    }
+  };
+  publish(0);
+  __syncthreads();
+  if (tid == 0) {
+    double m = 0.0;
+    for (int i = 0; i < 8; ++i) m = fmax(m, red[i]);
+    scal[0] = m;  // max |S|
+  }
+
+#ifdef DAV_TRIDIAG_PROFILE
+  long long cyc[4] = {0, 0, 0, 0};
+  long long ck0 = clock64();
+#define TRI_TICK(q) { const long long c1 = clock64(); if ((q) >= 0) cyc[(q) & 3] += c1 - ck0; ck0 = c1; }
+#if DAV_TRIDIAG_PROFILE == 1
+#define TRI_A(q) TRI_TICK(q)
+#define TRI_B(q)
+#else
+#define TRI_A(q)
+#define TRI_B(q) TRI_TICK(q)
+#endif
+#else
+#define TRI_TICK(q)
+#define TRI_A(q)
+#define TRI_B(q)
+#endif
+  for (int j = 0; j + 2 < k; ++j) {
+    const double tj = tjb;
+    const int last_row = ((ty | 1) + 1) * TS - 1;  // last row of this warp
+    const bool warp_live = last_row > j;           // some row of this warp is still in the trailing matrix
+    const bool tile_live = r0 + TS - 1 > j;  // (the interleaved columns of a tile stay live until the last steps)
+    double vc[TS], vr[TS];
+    if (tj != 0.0 && warp_live) {  // uniform per warp
+#pragma unroll
+      for (int q = 0; q < TS; q += 2) {
+        const double2 a = *reinterpret_cast<const double2*>(vb + col(q));
+        const double2 b = *reinterpret_cast<const double2*>(vb + r0 + q);
+        vc[q] = a.x; vc[q + 1] = a.y;
+        vr[q] = b.x; vr[q + 1] = b.y;
+      }
+      // ---- p = tau S v: row sums of my tile, reduce-scatter over the 16 tiles of the row
+      double pt[TS];
+#pragma unroll
+      for (int i = 0; i < TS; ++i) pt[i] = 0.0;
+      if (tile_live) {
+#pragma unroll
+        for (int i = 0; i < TS; ++i)
+#pragma unroll
+          for (int jj = 0; jj < TS; ++jj) pt[i] = fma(t[i][jj], vc[jj], pt[i]);
+      }
+      TRI_A(0)
+      const int idx = reduce_scatter16<TS>(pt, tx);
+      constexpr int WMASK = TS == 8 ? 1 : (TS == 4 ? 3 : 7);
+      if ((tx & WMASK) == 0) pb[r0 + idx] = (r0 + idx > j) ? pt[0] * tj : 0.0;
+    } else if (tj != 0.0 && last_row == j) {
+      if (tx < TS) pb[r0 + tx] = 0.0;  // this warp's rows just died: p stays exactly 0 there from now on
+    }
+    TRI_A(1)
+    TRI_B(3)
+    __syncthreads();
+    TRI_A(2)
+    TRI_B(3)
+    if (tj != 0.0 && warp_live) {
+      double pc[TS], pr[TS];
+      double pvp = 0.0;
+#pragma unroll
+      for (int q = 0; q < TS; q += 2) {
+        const double2 a = *reinterpret_cast<const double2*>(pb + col(q));
+        const double2 b = *reinterpret_cast<const double2*>(pb + r0 + q);
+        pc[q] = a.x; pc[q + 1] = a.y;
+        pr[q] = b.x; pr[q + 1] = b.y;
+      }
+#pragma unroll
+      for (int q = 0; q < TS; ++q) pvp = fma(pc[q], vc[q], pvp);
+      const double pv = allreduce16(pvp);
+      const double K = -0.5 * tj * pv;
+      TRI_B(0)
+      if (tile_live) {
+        // w = p + K v is 0 wherever v and p are (dead rows / columns): those entries are never touched again
+#pragma unroll
+        for (int q = 0; q < TS; ++q) {
+          pc[q] = fma(K, vc[q], pc[q]);
+          pr[q] = fma(K, vr[q], pr[q]);
+        }
+#pragma unroll
+        for (int i = 0; i < TS; ++i)
+#pragma unroll
+          for (int jj = 0; jj < TS; ++jj) t[i][jj] = fma(-pr[i], vc[jj], fma(-vr[i], pc[jj], t[i][jj]));
+      }
+    }
+    TRI_B(1)
+    publish(j + 1);
+    TRI_B(2)
+    __syncthreads();
+    TRI_A(3)
+    TRI_B(3)
+  }
+#ifdef DAV_TRIDIAG_PROFILE
+  if (tid == 255) for (int q = 0; q < 4; ++q) scal[3 + q] = (double)cyc[q];
+#endif
+#undef TRI_TICK
+#undef TRI_A
+#undef TRI_B
+  // the last 2 x 2 block and the trivial reflectors
+#pragma unroll
+  for (int i = 0; i < TS; ++i)
+#pragma unroll
+    for (int jj = 0; jj < TS; ++jj) {
+      const int a = r0 + i, c = col(jj);
+      if (k >= 2 && a == k - 2 && c == k - 2) { d[k - 2] = t[i][jj]; tau[k - 2] = 0.0; }
+      if (k >= 2 && a == k - 2 && c == k - 1) e[k - 2] = t[i][jj];
+      if (a == k - 1 && c == k - 1) { d[k - 1] = t[i][jj]; tau[k - 1] = 0.0; }
+    }
+}
+
 // ---- 2. one warp per eigenpair ----------------------------------------------------------------------------------
 constexpr int EW = 8;  // warps per CTA
 
@@ -238,7 +499,7 @@ __global__ void __launch_bounds__(EW * 32) tri_eigvec_kernel(int k, const double
                                                             const double* __restrict__ e_in,
                                                             const double* __restrict__ Vh,
                                                             const double* __restrict__ tau, double* __restrict__ Y,
-                                                            double* __restrict__ lam_out) {
+                                                            double* __restrict__ lam_out, int vh_smem) {
   extern __shared__ __align__(16) double sm[];
   // T is scaled to unit norm (ds = d / tn, es = e / tn): counts and eigenvectors are scale invariant, and the
   // characteristic-polynomial recurrence below can then grow by at most 3x per step
@@ -251,6 +512,16 @@ __global__ void __launch_bounds__(EW * 32) tri_eigvec_kernel(int k, const double
   double* z = qm + k;
   double* fa = z + k;                           // forward denominators, then the upward coefficients
   double* fb = fa + k;                          // backward denominators, then the downward coefficients
+  // r02: the k x k reflector block staged in shared memory when it fits (k <= 128), copied asynchronously while the
+  // eigenvalue is being located.  From global memory every one of the k-2 back-transformation steps waited for an
+  // L2 round trip (one reflector of prefetch hides ~180 of ~700 cycles): 109 us at k = 128, of which ~60 us latency.
+  double* vhs = e2s + k + (size_t)EW * 5 * k;
+  if (vh_smem) {
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(vhs);
+    for (int idx = threadIdx.x; idx < k * k; idx += blockDim.x)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sbase + 8u * (unsigned)idx), "l"(Vh + idx) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   // Gershgorin interval and norm (every warp computes the same values)
   double gl = 1.0e300, gu = -1.0e300;
   for (int i = lane; i < k; i += 32) {
@@ -272,8 +543,9 @@ __global__ void __launch_bounds__(EW * 32) tri_eigvec_kernel(int k, const double
     e2s[i] = ei * ei;
   }
   __syncthreads();
-  const int j = blockIdx.x * EW + warp;  // eigenvalue index (ascending)
-  if (j >= k) return;
+  const int jraw = blockIdx.x * EW + warp;  // eigenvalue index (ascending)
+  const bool valid = jraw < k;              // idle warps of the last CTA compute a duplicate and store nothing
+  const int j = valid ? jraw : k - 1;
 
   // ---- eigenvalue j by 32-way multisection.  count(x) = #{eigenvalues < x} = sign changes of the Sturm sequence
   // p_0 = 1, p_1 = d_0 - x, p_{i+1} = (d_i - x) p_i - e_{i-1}^2 p_{i-1}  (one dependent FMA per step; a zero takes
@@ -394,18 +666,23 @@ __global__ void __launch_bounds__(EW * 32) tri_eigvec_kernel(int k, const double
   for (int t = 0; t < KT; ++t) zr[t] *= inv;
 
   // ---- back-transformation y = H_0 H_1 ... H_{k-3} z, reflectors applied last to first
+  if (vh_smem) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+  }
+  const double* VhP = vh_smem ? vhs : Vh;
   double vc[KT], vn[KT];
   int jj = k - 3;
 #pragma unroll
   for (int t = 0; t < KT; ++t) {
     const int a = lane + 32 * t;
-    vc[t] = (jj >= 0 && a < k) ? Vh[(size_t)jj * k + a] : 0.0;
+    vc[t] = (jj >= 0 && a < k) ? VhP[(size_t)jj * k + a] : 0.0;
   }
   for (; jj >= 0; --jj) {
 #pragma unroll
     for (int t = 0; t < KT; ++t) {
       const int a = lane + 32 * t;
-      vn[t] = (jj >= 1 && a < k) ? Vh[(size_t)(jj - 1) * k + a] : 0.0;  // prefetch the next reflector
+      vn[t] = (jj >= 1 && a < k) ? VhP[(size_t)(jj - 1) * k + a] : 0.0;  // prefetch the next reflector
     }
     const double tj = tau[jj];
     double dot = 0.0;
@@ -418,6 +695,7 @@ __global__ void __launch_bounds__(EW * 32) tri_eigvec_kernel(int k, const double
       vc[t] = vn[t];
     }
   }
+  if (!valid) return;
 #pragma unroll
   for (int t = 0; t < KT; ++t) {
     const int a = lane + 32 * t;
@@ -552,7 +830,9 @@ double* sym_eigh_flags(double* scratch, int k) {
 }
 
 bool sym_eigh_uses_tridiag(int k) {
-  static const int min_k = env_int("DAV_EIGH_TRIDIAG_MIN_K", 48);
+  // r02: with the register-resident tridiagonalisation the fast path wins from k = 16 on (k = 32: 0.093 ms against
+  // 0.284 ms for the one-CTA Jacobi; profiles/r02_eigh_bench*)
+  static const int min_k = env_int("DAV_EIGH_TRIDIAG_MIN_K", 16);
   return k >= min_k && k <= 512;
 }
 
@@ -585,27 +865,38 @@ void sym_eigh(cudaStream_t s, int k, double* S, double* Y, double* w, double* sc
   double* flagv = lam + k;        // [0] max|S|, [1] max|G - I|, [2] max residual
   int* accept = reinterpret_cast<int*>(flagv + 8);
 
-  // the step loop is instruction-issue bound on per-warp bookkeeping, not on the m^2 FMAs: few warps for small k
-  static const int thr_env = env_int("DAV_TRIDIAG_THREADS", 0);
-  // (measured: k = 64 -> 256 threads, k = 128/160 -> 512, k >= 256 -> 1024; the row mapping needs >= k/32 warps)
-  int threads = thr_env > 0 ? thr_env : (k <= 64 ? 256 : (k <= 160 ? 512 : 1024));
-  threads = std::min(1024, std::max(threads, 32 * ((k + 31) / 32)));
-  const size_t small = 32 + 4 + 3 * (size_t)k + (size_t)threads;
-  const size_t need_in = (small + kk) * sizeof(double);
-  const int s_in = need_in <= (size_t)max_smem - 2048 ? 1 : 0;  // 2 KB of static tables
-  const size_t tsm = s_in ? need_in : small * sizeof(double);
-  if (k <= 64) tridiag_kernel<2><<<1, threads, tsm, s>>>(k, S, work, s_in, Sfull, Vh, tau, d, e, flagv);
-  else if (k <= 160) tridiag_kernel<5><<<1, threads, tsm, s>>>(k, S, work, s_in, Sfull, Vh, tau, d, e, flagv);
-  else tridiag_kernel<8><<<1, threads, tsm, s>>>(k, S, work, s_in, Sfull, Vh, tau, d, e, flagv);
+  static const int reg_env = env_int("DAV_TRIDIAG_REG", 1);
+  if (reg_env != 0 && k <= 128) {
+    // register-resident matrix (r02): 16 x 16 threads, TS x TS tile each
+    if (k <= 32) tridiag_reg_kernel<2><<<1, 256, 0, s>>>(k, S, Sfull, Vh, tau, d, e, flagv);
+    else if (k <= 64) tridiag_reg_kernel<4><<<1, 256, 0, s>>>(k, S, Sfull, Vh, tau, d, e, flagv);
+    else tridiag_reg_kernel<8><<<1, 256, 0, s>>>(k, S, Sfull, Vh, tau, d, e, flagv);
+  } else {
+    // the step loop is instruction-issue bound on per-warp bookkeeping, not on the m^2 FMAs: few warps for small k
+    static const int thr_env = env_int("DAV_TRIDIAG_THREADS", 0);
+    // (measured: k = 64 -> 256 threads, k = 128/160 -> 512, k >= 256 -> 1024; the row mapping needs >= k/32 warps)
+    int threads = thr_env > 0 ? thr_env : (k <= 64 ? 256 : (k <= 160 ? 512 : 1024));
+    threads = std::min(1024, std::max(threads, 32 * ((k + 31) / 32)));
+    const size_t small = 32 + 4 + 3 * (size_t)k + (size_t)threads;
+    const size_t need_in = (small + kk) * sizeof(double);
+    const int s_in = need_in <= (size_t)max_smem - 2048 ? 1 : 0;  // 2 KB of static tables
+    const size_t tsm = s_in ? need_in : small * sizeof(double);
+    if (k <= 64) tridiag_kernel<2><<<1, threads, tsm, s>>>(k, S, work, s_in, Sfull, Vh, tau, d, e, flagv);
+    else if (k <= 160) tridiag_kernel<5><<<1, threads, tsm, s>>>(k, S, work, s_in, Sfull, Vh, tau, d, e, flagv);
+    else tridiag_kernel<8><<<1, threads, tsm, s>>>(k, S, work, s_in, Sfull, Vh, tau, d, e, flagv);
+  }
   CK_LAUNCH();
   ++g_kernel_launches;
   {
     const int grid = (k + EW - 1) / EW;
-    const size_t sm = (3 + 5 * (size_t)EW) * k * sizeof(double);
-    if (k <= 64) tri_eigvec_kernel<2><<<grid, EW * 32, sm, s>>>(k, d, e, Vh, tau, Yraw, lam);
-    else if (k <= 128) tri_eigvec_kernel<4><<<grid, EW * 32, sm, s>>>(k, d, e, Vh, tau, Yraw, lam);
-    else if (k <= 256) tri_eigvec_kernel<8><<<grid, EW * 32, sm, s>>>(k, d, e, Vh, tau, Yraw, lam);
-    else tri_eigvec_kernel<16><<<grid, EW * 32, sm, s>>>(k, d, e, Vh, tau, Yraw, lam);
+    size_t sm = (3 + 5 * (size_t)EW) * k * sizeof(double);
+    static const int vhs_env = env_int("DAV_EIGVEC_VH_SMEM", 1);
+    const int vh_smem = (vhs_env != 0 && sm + kk * sizeof(double) <= (size_t)max_smem) ? 1 : 0;
+    if (vh_smem) sm += kk * sizeof(double);
+    if (k <= 64) tri_eigvec_kernel<2><<<grid, EW * 32, sm, s>>>(k, d, e, Vh, tau, Yraw, lam, vh_smem);
+    else if (k <= 128) tri_eigvec_kernel<4><<<grid, EW * 32, sm, s>>>(k, d, e, Vh, tau, Yraw, lam, vh_smem);
+    else if (k <= 256) tri_eigvec_kernel<8><<<grid, EW * 32, sm, s>>>(k, d, e, Vh, tau, Yraw, lam, vh_smem);
+    else tri_eigvec_kernel<16><<<grid, EW * 32, sm, s>>>(k, d, e, Vh, tau, Yraw, lam, vh_smem);
     CK_LAUNCH();
     ++g_kernel_launches;
   }
