@@ -25,7 +25,7 @@ SYMBOLS = [
     "dav_lapack_generalized_eigensolver_lowest", "dav_sym_eigh_info", "dav_lapack_qr", "dav_lapack_solver", "dav_lapack_matmul",
     "dav_lapack_matrix_vector", "dav_lapack_sort", "dav_free_matmul", "dav_compute_on_the_fly",
     "dav_debug_matvec_schedule", "dav_bench_fp64_pipe", "dav_debug_matvec_rect", "dav_debug_collective",
-    "dav_comm_info", "dav_debug_chol_inv", "dav_debug_gemm_bench",
+    "dav_comm_info", "dav_debug_chol_inv", "dav_debug_gemm_bench", "dav_debug_pip_small",
 ]
 
 
@@ -38,6 +38,7 @@ class Stats(C.Structure):
         ("resid_ms", C.c_double), ("proj_ms", C.c_double), ("init_ms", C.c_double),
         ("gjd_inner_iterations", C.c_int), ("gather_ms", C.c_double), ("output_ms", C.c_double),
         ("comm_ms", C.c_double), ("collectives", C.c_int), ("spans_dropped", C.c_int), ("peer_transport", C.c_int),
+        ("pip_fallbacks", C.c_int),
     ]
 
 

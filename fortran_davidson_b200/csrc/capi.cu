@@ -404,6 +404,23 @@ int dav_debug_chol_inv(int b, const double* g, double* t, double* flag, float* m
   API_END
 }
 
+int dav_debug_pip_small(int mode, int kold, int b, const double* gall, double* z, double* metrics, int* launched) {
+  API_BEGIN
+  need((mode == 0 || mode == 1) && kold >= 1 && b >= 1 && gall && z && metrics && launched, "bad arguments");
+  Ctx c;
+  const size_t cnt = (size_t)(kold + b) * b;
+  DevBuf<double> G, Z, M;
+  G.alloc(cnt); Z.alloc(cnt); M.alloc(4);
+  h2d(G.p, gall, cnt, c.s);
+  CK(cudaMemsetAsync(Z.p, 0, cnt * 8, c.s));
+  CK(cudaMemsetAsync(M.p, 0, 4 * 8, c.s));
+  *launched = pip_small(c.s, mode, kold, b, G.p, Z.p, M.p) ? 1 : 0;
+  d2h(z, Z.p, cnt, c.s);
+  d2h(metrics, M.p, 4, c.s);
+  c.sync();
+  API_END
+}
+
 int dav_debug_gemm_bench(char transA, int64_t m, int64_t n, int64_t k, int reps, int to_partials, float* ms_out,
                          double* max_err) {
   API_BEGIN

@@ -143,7 +143,9 @@ __global__ void __launch_bounds__(128 * KG) gemm_dmma_kernel(int64_t M, int64_t 
                                                              double alpha, const double* __restrict__ A, int64_t lda,
                                                              const double* __restrict__ B, int64_t ldb, double beta,
                                                              double* __restrict__ C, int64_t ldc,
-                                                             double* __restrict__ ws, int splits, int to_ws) {
+                                                             double* __restrict__ ws, int splits, int to_ws,
+                                                             const double* __restrict__ A2, int64_t lda2,
+                                                             int64_t asplit) {
   extern __shared__ __align__(16) double red_sm[];
   constexpr int WMS = 4 / WNS;
   constexpr int UN = KG == 4 ? 2 : UN_MAX;  // 512 threads leave 128 registers per thread: two k-steps in flight
@@ -169,16 +171,36 @@ __global__ void __launch_bounds__(128 * KG) gemm_dmma_kernel(int64_t M, int64_t 
 
   if (active && gb < ge) {
     // per-lane base pointers (clamped to a valid row / column) of the four m-tiles / n-tiles
+    // op(A) may be given as TWO blocks (A2 != nullptr): TN -- columns [0, asplit) of A^T's row index m come from A,
+    // [asplit, M) from A2 (the Gram / projection of [V | T] in one product); NN -- columns [0, asplit) of A from A,
+    // [asplit, K) from A2 (the update [V | T] * Z in one product; asplit is a multiple of 4 there).
     const double* ap[4];
     const double* bp[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int64_t m = min(m0 + 8 * i + g, M - 1);
-      ap[i] = TA ? A + m * lda + t : A + m + (int64_t)t * lda;
+      if (TA) ap[i] = (A2 != nullptr && m >= asplit) ? A2 + (m - asplit) * lda2 + t : A + m * lda + t;
+      else ap[i] = A + m + (int64_t)t * lda;
       const int64_t n = min(n0 + 8 * i + g, N - 1);
       bp[i] = B + n * ldb + t;
     }
-    const int64_t astep = TA ? 1 : lda;  // distance between consecutive k in op(A)
+    int64_t astep = TA ? 1 : lda;  // distance between consecutive k in op(A)
+    const int nseg = (!TA && A2 != nullptr) ? 2 : 1;
+    for (int seg = 0; seg < nseg; ++seg) {
+    int64_t sb = gb, se = ge;  // this segment of the warp group's K range
+    if (nseg == 2) {
+      if (seg == 0) se = min(ge, asplit);
+      else {
+        sb = max(gb, asplit);
+        astep = lda2;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int64_t m = min(m0 + 8 * i + g, M - 1);
+          ap[i] = A2 + m + ((int64_t)t - asplit) * lda2;  // indexed with the global k below
+        }
+      }
+      if (sb >= se) continue;
+    }
     // which 8-wide tiles of this warp exist at all (warp-uniform): skipped MMAs for N = 16, edge tiles
     bool mi[4], nj[4];
 #pragma unroll
@@ -186,13 +208,13 @@ __global__ void __launch_bounds__(128 * KG) gemm_dmma_kernel(int64_t M, int64_t 
       mi[i] = m0 + 8 * i < M;
       nj[i] = n0 + 8 * i < N;
     }
-    int64_t kk = gb;
+    int64_t kk = sb;
     if (VEC) {
       // TN, 16-byte aligned operands: the order of the k index inside an MMA is free as long as A and B agree, so
       // lane t takes 2 VH CONSECUTIVE rows of its column with VH 16-byte loads and feeds one of them to each of the
       // chunk's 2 VH MMAs -- half as many load instructions (and L1 wavefronts) per flop
       constexpr int VH = KG == 4 ? 1 : 2;  // 16-byte loads per tile and chunk (512 threads: 128 registers each)
-      for (; kk + 8 * VH <= ge; kk += 8 * VH) {
+      for (; kk + 8 * VH <= se; kk += 8 * VH) {
         double2 a[4][VH], b[4][VH];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -219,7 +241,7 @@ __global__ void __launch_bounds__(128 * KG) gemm_dmma_kernel(int64_t M, int64_t 
           }
       }
     }
-    for (; kk + 4 * UN <= ge; kk += 4 * UN) {
+    for (; kk + 4 * UN <= se; kk += 4 * UN) {
       double a[UN][4], b[UN][4];
 #pragma unroll
       for (int u = 0; u < UN; ++u)
@@ -242,8 +264,8 @@ __global__ void __launch_bounds__(128 * KG) gemm_dmma_kernel(int64_t M, int64_t 
           }
         }
     }
-    for (; kk < ge; kk += 4) {  // tail: fewer than 4 UN rows left, the last k-step may be partial
-      const bool kin = kk + t < ge;
+    for (; kk < se; kk += 4) {  // tail: fewer than 4 UN rows left, the last k-step may be partial
+      const bool kin = kk + t < se;
       double a[4], b[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -262,6 +284,7 @@ __global__ void __launch_bounds__(128 * KG) gemm_dmma_kernel(int64_t M, int64_t 
         }
       }
     }
+    }  // segments
   }
 
   // sum of the KG warp groups, fixed tree order: (g0 + g2) + (g1 + g3) for KG = 4, g0 + g1 for KG = 2
@@ -343,11 +366,11 @@ namespace {
 template <bool TA, int KG, int WNS, bool VEC>
 void launch_dmma(cudaStream_t s, dim3 grid, int64_t M, int64_t N, int64_t K, int64_t Kchunk, double alpha,
                  const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
-                 double* ws, int splits, int to_ws) {
+                 double* ws, int splits, int to_ws, const double* A2, int64_t lda2, int64_t asplit) {
   const size_t sm = KG > 1 ? (size_t)(KG / 2) * 4 * 32 * 32 * sizeof(double) : 0;
   if (sm > 48 * 1024) ensure_dyn_smem(gemm_dmma_kernel<TA, KG, WNS, VEC>, (int)sm);
-  gemm_dmma_kernel<TA, KG, WNS, VEC><<<grid, 128 * KG, sm, s>>>(M, N, K, Kchunk, alpha, A, lda, B, ldb, beta, C, ldc, ws,
-                                                          splits, to_ws);
+  gemm_dmma_kernel<TA, KG, WNS, VEC><<<grid, 128 * KG, sm, s>>>(M, N, K, Kchunk, alpha, A, lda, B, ldb, beta, C, ldc,
+                                                               ws, splits, to_ws, A2, lda2, asplit);
 }
 int env_or(const char* name, int dflt) {
   const char* e = std::getenv(name);
@@ -357,7 +380,7 @@ int env_or(const char* name, int dflt) {
 
 void gemm(cudaStream_t s, bool transA, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
           const double* B, int64_t ldb, double beta, double* C, int64_t ldc, double* ws, size_t ws_doubles,
-          int* partials_out) {
+          int* partials_out, const GemmSplit* split) {
   if (M <= 0 || N <= 0) {
     if (partials_out) *partials_out = 0;
     return;
@@ -367,7 +390,14 @@ void gemm(cudaStream_t s, bool transA, int64_t M, int64_t N, int64_t K, double a
               (long long)N);
   const int to_ws = partials_out ? 1 : 0;
   // read per call so one process can compare the implementations (tests, bench A/B)
-  const int impl = env_or("DAV_GEMM_IMPL", GEMM_IMPL_DEFAULT);
+  int impl = env_or("DAV_GEMM_IMPL", GEMM_IMPL_DEFAULT);
+  const double* A2 = split ? split->A2 : nullptr;
+  const int64_t lda2 = split ? split->lda2 : 0, asplit = split ? split->at : 0;
+  if (A2) {
+    impl = 1;  // the two-block operand exists on the tensor-pipe kernel only
+    if (asplit <= 0 || asplit >= (transA ? M : K) || (!transA && asplit % 4 != 0))
+      DAV_THROW(DAV_ERR_INVALID, "gemm: bad operand split %lld", (long long)asplit);
+  }
   // tensor-pipe kernel: 128 x 32 CTA tiles for blocks of <= 32 columns, 64 x 64 otherwise
   const int wns = (impl == 1 && N <= 32) ? 1 : 2;
   const int bm = impl == 1 ? 32 * (4 / wns) : BM, bn = impl == 1 ? 32 * wns : BN;
@@ -399,9 +429,11 @@ void gemm(cudaStream_t s, bool transA, int64_t M, int64_t N, int64_t K, double a
     // thousands of CTAs) are faster with 4-warp CTAs and no shared-memory sum (measured, profiles/r02_gemm_bench*)
     if (kg == 0) kg = (transA && Kchunk >= 256) ? 4 : 1;
     const bool vec = transA && env_or("DAV_GEMM_VEC", 1) != 0 && lda % 2 == 0 && ldb % 2 == 0 &&
-                     (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0;
+                     (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
+                     (!A2 || (lda2 % 2 == 0 && (reinterpret_cast<uintptr_t>(A2) & 15) == 0));
 #define DAV_GEMM_CASE(TA_, KG_, WNS_, VEC_)                                                                         \
-  launch_dmma<TA_, KG_, WNS_, VEC_>(s, grid, M, N, K, Kchunk, alpha, A, lda, B, ldb, beta, C, ldc, ws, splits, to_ws)
+  launch_dmma<TA_, KG_, WNS_, VEC_>(s, grid, M, N, K, Kchunk, alpha, A, lda, B, ldb, beta, C, ldc, ws, splits, to_ws, \
+                                    A2, lda2, asplit)
 #define DAV_GEMM_KG(TA_, WNS_, VEC_)                                   \
   do {                                                                 \
     if (kg == 4) DAV_GEMM_CASE(TA_, 4, WNS_, VEC_);                    \

@@ -15,9 +15,16 @@ extern thread_local long long g_kernel_launches;
 // partials_out != nullptr: the product (alpha = 1, beta = 0 implied) is LEFT as *partials_out partial blocks of
 // M x N doubles in ws (ws[z*M*N + m + j*M]) and C is not touched: the caller sums them -- Comm::reduce_sum does that
 // together with the sum over the ranks and the output layout in one kernel.
+// split != nullptr: op(A) is given as two blocks -- TN: rows [0, at) of the result come from A, [at, M) from A2
+// (both K x . with their own leading dimension); NN: columns [0, at) of A from A, [at, K) from A2 (at % 4 == 0).
+struct GemmSplit {
+  const double* A2;
+  int64_t lda2;
+  int64_t at;
+};
 void gemm(cudaStream_t s, bool transA, int64_t M, int64_t N, int64_t K, double alpha, const double* A,
           int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, double* ws,
-          size_t ws_doubles, int* partials_out = nullptr);
+          size_t ws_doubles, int* partials_out = nullptr, const GemmSplit* split = nullptr);
 
 // ---- matvec_dmma.cu : the hot kernel.  W(M x b) = A(M x K, lda) * X(K x b)  ---------------------
 // TMA (2D tensor map, 128B swizzle) -> mbarrier pipeline -> FP64 DMMA, persistent stream-K grid.
@@ -99,6 +106,11 @@ bool chol_inv_upper(cudaStream_t s, int b, const double* G, double* T, double* f
 void pip_prepare(cudaStream_t s, int k, int b, const double* Gall, const double* P, double* Gs, double* D,
                  double* metrics);
 void pip_finish(cudaStream_t s, int k, int b, const double* Tinv, const double* D, double* Tm, double* M);
+// the five calls above (small GEMM H^T H, pip_prepare, chol_inv_upper, pip_finish, small GEMM -H Tm) in ONE kernel:
+// Gall ((kold + b) x b) -> Z = [-H Tm; Tm], metrics[0..3] (see smalldense.cu).  mode 0: first pass (scaled Cholesky),
+// mode 1: second pass (Tm = (I + E)^-1/2 by its series; metrics[2] raised when |E| >= 1e-5).  Returns false (nothing
+// launched) when the block does not fit one CTA's shared memory: the caller then uses the separate kernels.
+bool pip_small(cudaStream_t s, int mode, int kold, int b, const double* Gall, double* Z, double* metrics);
 // Rinv = inverse of the upper triangular R (k x k)
 void invert_upper(cudaStream_t s, int k, const double* R, int64_t ld, double* Rinv);
 

@@ -568,6 +568,105 @@ __global__ void __launch_bounds__(512) chol_inv_upper_kernel(int b, const double
 // Phase 2, R^-1 by the column operations that turn R into I applied to an identity kept in the same registers
 // (X(:,j) /= R(j,j); X(:,c) -= X(:,j) R(j,c)), same look-ahead.  ~2b barrier-separated steps of 16 FMAs per thread
 // instead of b steps of index arithmetic plus a thread-per-column back substitution: 110 -> ~10 us at b = 64.
+// body shared by chol_inv_tile_kernel and the fused pip_small_kernel: `active` threads (tid < T*T) hold the tile t of
+// the symmetric matrix (both triangles filled, identity padding beyond b) and d0 = its original diagonal entries;
+// on return t holds R^-1 (valid for row <= column) unless *bad.  Every thread of the CTA must call it (barriers).
+__device__ __forceinline__ void chol_inv_tile_body(int T, bool active, int tx, int ty, double (&t)[4][4],
+                                                   const double (&d0)[4], double* Rs, double* buf, double* rinv_s,
+                                                   int* bad) {
+  const int bp = 4 * T;
+  const int r0 = 4 * ty, c0 = 4 * tx;
+  // phase 1 look-ahead: row jn (unscaled) and 1/sqrt(pivot jn)
+  auto publish_row = [&](int jn) {
+    if (!active || ty != (jn >> 2)) return;
+    const int i = jn & 3;
+    double* rb = buf + (jn & 1) * bp;
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii)
+      if (ii == i) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) rb[c0 + jj] = t[ii][jj];
+        if (tx == ty) {
+          const double d = t[ii][ii];
+          // pivot must stay well above the round-off of the eliminations (cond(G) < ~1e12)
+          if (!(d > 1e-12 * fabs(d0[ii])) || !(d0[ii] > 0.0)) {
+            *bad = 1;
+            rinv_s[jn] = 0.0;
+          } else {
+            rinv_s[jn] = rsqrt(d);
+          }
+        }
+      }
+  };
+  publish_row(0);
+  for (int j = 0; j < bp; ++j) {
+    __syncthreads();
+    if (*bad) break;  // uniform
+    const double* rb = buf + (j & 1) * bp;
+    const double rinv = rinv_s[j];
+    if (active && ty == (j >> 2)) {
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) Rs[(size_t)j * bp + c0 + jj] = rb[c0 + jj] * rinv;
+    }
+    if (active && r0 + 3 > j && c0 + 3 > j) {
+      const double dinv = rinv * rinv;
+      double ra[4], rc[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        ra[i] = (r0 + i > j) ? rb[r0 + i] * dinv : 0.0;
+        rc[i] = (c0 + i > j) ? rb[c0 + i] : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) t[i][jj] = fma(-ra[i], rc[jj], t[i][jj]);
+    }
+    if (j + 1 < bp) publish_row(j + 1);
+  }
+  __syncthreads();
+  if (*bad) return;
+
+  // phase 2: X = R^-1 in the same registers
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) t[i][jj] = (r0 + i == c0 + jj) ? 1.0 : 0.0;
+  auto publish_col = [&](int jn) {  // column jn scaled by 1 / R(jn, jn)
+    if (!active || tx != (jn >> 2)) return;
+    const int jj = jn & 3;
+    const double rinv = rinv_s[jn];
+    double* xb = buf + (jn & 1) * bp;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q == jj) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          t[i][q] *= rinv;
+          xb[r0 + i] = t[i][q];
+        }
+      }
+  };
+  publish_col(0);
+  for (int j = 0; j < bp; ++j) {
+    __syncthreads();
+    if (active && c0 + 3 > j && r0 <= j) {  // X(a, j) = 0 for a > j
+      const double* xb = buf + (j & 1) * bp;
+      const double* rj = Rs + (size_t)j * bp;
+      double xa[4], rc[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        xa[i] = xb[r0 + i];
+        rc[i] = (c0 + i > j) ? rj[c0 + i] : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) t[i][jj] = fma(-xa[i], rc[jj], t[i][jj]);
+    }
+    if (j + 1 < bp) publish_col(j + 1);
+  }
+}
+
 __global__ void __launch_bounds__(1024) chol_inv_tile_kernel(int b, const double* __restrict__ G,
                                                              double* __restrict__ Tout, double* __restrict__ flag) {
   extern __shared__ __align__(16) double sm[];
@@ -591,98 +690,10 @@ __global__ void __launch_bounds__(1024) chol_inv_tile_kernel(int b, const double
   for (int i = 0; i < 4; ++i) d0[i] = t[i][i];  // meaningful on the diagonal threads only
   if (threadIdx.x == 0) bad = 0;
   __syncthreads();
-
-  // phase 1 look-ahead: row jn (unscaled) and 1/sqrt(pivot jn)
-  auto publish_row = [&](int jn) {
-    if (ty != (jn >> 2)) return;
-    const int i = jn & 3;
-    double* rb = buf + (jn & 1) * bp;
-#pragma unroll
-    for (int ii = 0; ii < 4; ++ii)
-      if (ii == i) {
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) rb[c0 + jj] = t[ii][jj];
-        if (tx == ty) {
-          const double d = t[ii][ii];
-          // pivot must stay well above the round-off of the eliminations (cond(G) < ~1e12)
-          if (!(d > 1e-12 * fabs(d0[ii])) || !(d0[ii] > 0.0)) {
-            bad = 1;
-            rinv_s[jn] = 0.0;
-          } else {
-            rinv_s[jn] = rsqrt(d);
-          }
-        }
-      }
-  };
-  publish_row(0);
-  for (int j = 0; j < bp; ++j) {
-    __syncthreads();
-    if (bad) break;  // uniform
-    const double* rb = buf + (j & 1) * bp;
-    const double rinv = rinv_s[j];
-    if (ty == (j >> 2)) {
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) Rs[(size_t)j * bp + c0 + jj] = rb[c0 + jj] * rinv;
-    }
-    if (r0 + 3 > j && c0 + 3 > j) {
-      const double dinv = rinv * rinv;
-      double ra[4], rc[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        ra[i] = (r0 + i > j) ? rb[r0 + i] * dinv : 0.0;
-        rc[i] = (c0 + i > j) ? rb[c0 + i] : 0.0;
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) t[i][jj] = fma(-ra[i], rc[jj], t[i][jj]);
-    }
-    if (j + 1 < bp) publish_row(j + 1);
-  }
-  __syncthreads();
+  chol_inv_tile_body(T, true, tx, ty, t, d0, Rs, buf, rinv_s, &bad);
   if (bad) {
     if (threadIdx.x == 0) flag[0] = 1.0;
     return;
-  }
-
-  // phase 2: X = R^-1 in the same registers
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) t[i][jj] = (r0 + i == c0 + jj) ? 1.0 : 0.0;
-  auto publish_col = [&](int jn) {  // column jn scaled by 1 / R(jn, jn)
-    if (tx != (jn >> 2)) return;
-    const int jj = jn & 3;
-    const double rinv = rinv_s[jn];
-    double* xb = buf + (jn & 1) * bp;
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (q == jj) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          t[i][q] *= rinv;
-          xb[r0 + i] = t[i][q];
-        }
-      }
-  };
-  publish_col(0);
-  for (int j = 0; j < bp; ++j) {
-    __syncthreads();
-    if (c0 + 3 > j && r0 <= j) {  // X(a, j) = 0 for a > j
-      const double* xb = buf + (j & 1) * bp;
-      const double* rj = Rs + (size_t)j * bp;
-      double xa[4], rc[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        xa[i] = xb[r0 + i];
-        rc[i] = (c0 + i > j) ? rj[c0 + i] : 0.0;
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) t[i][jj] = fma(-xa[i], rc[jj], t[i][jj]);
-    }
-    if (j + 1 < bp) publish_col(j + 1);
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -768,6 +779,195 @@ __global__ void pip_finish_kernel(int k, int b, const double* __restrict__ Tinv,
   }
 }
 
+// ---- r02: everything between the tall-skinny products of one BCGS-PIP pass in ONE kernel (was: small GEMM H^T H,
+// pip_prepare, chol_inv_upper, pip_finish, small GEMM H * Tm = 5 launches, 56 us at b = 32 and 103 us at b = 64).
+// Gall ((kold + b) x b, ld kold + b): rows 0..kold = H = V^T C, rows kold.. = C^T C.  Z (same shape) <- [-H Tm; Tm]
+// with Tm^T (C^T C - H^T H) Tm = I:
+//   MODE 0 (first pass)   Tm = D R^-1, D G' D = R^T R: scaled Cholesky + inverse on the register tiles below
+//   MODE 1 (second pass)  the block is already orthonormal to ~eps cond^2, G' = I + E with |E| << 1:
+//                         Tm = (I + E)^-1/2 = I - E/2 + 3/8 E^2 + O(E^3) -- no factorisation, no sequential steps;
+//                         metrics[2] is raised when |E| >= 1e-5 (the caller then takes the fallback path)
+// metrics[0] = max |H_kj| / sqrt((C^T C)_jj), [1] = max |D G' D - I| (MODE 1: max |E|), [2] = 1.0 when a diagonal
+// entry of G' is not safely positive, [3] = 1.0 when a Cholesky pivot is unsafe.
+template <int MODE, int NTMAX>
+__global__ void __launch_bounds__(NTMAX) pip_small_kernel(int kold, int b, const double* __restrict__ Gall,
+                                                         double* __restrict__ Z, double* __restrict__ metrics) {
+  extern __shared__ __align__(16) double sm[];
+  const int T = (b + 3) >> 2, bp = 4 * T, ld = kold + b;
+  double* Hs = sm;                       // kold x bp row-major: Hs[k * bp + j] = H(k, j), 0 for j >= b
+  double* W1 = Hs + (size_t)kold * bp;   // bp x bp: rows of R (MODE 0) / E (MODE 1)
+  double* W2 = W1 + (size_t)bp * bp;     // bp x bp row-major: Tm
+  double* buf = W2 + (size_t)bp * bp;    // 2 bp
+  double* rinv_s = buf + 2 * bp;         // bp
+  double* dsc = rinv_s + bp;             // bp: D = diag(G')^-1/2 (MODE 1: 1)
+  double* cn = dsc + bp;                 // bp: 1 / sqrt((C^T C)_jj)
+  __shared__ double red[32];
+  __shared__ int bad, badd;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const bool active = tid < T * T;
+  const int tx = tid % T, ty = tid / T;
+  const int r0 = 4 * ty, c0 = 4 * tx;
+  if (tid == 0) { bad = 0; badd = 0; }
+  for (int e = tid; e < kold * bp; e += nt) {
+    const int k = e / bp, j = e - k * bp;
+    Hs[e] = j < b ? Gall[(size_t)j * ld + k] : 0.0;
+  }
+  __syncthreads();
+
+  // G' = C^T C - H^T H on the 4 x 4 register tiles of the T x T thread grid
+  double t[4][4], d0[4];
+  if (active) {
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) acc[i][jj] = 0.0;
+    for (int k = 0; k < kold; ++k) {
+      const double2 a01 = *reinterpret_cast<const double2*>(Hs + (size_t)k * bp + r0);
+      const double2 a23 = *reinterpret_cast<const double2*>(Hs + (size_t)k * bp + r0 + 2);
+      const double2 b01 = *reinterpret_cast<const double2*>(Hs + (size_t)k * bp + c0);
+      const double2 b23 = *reinterpret_cast<const double2*>(Hs + (size_t)k * bp + c0 + 2);
+      const double a[4] = {a01.x, a01.y, a23.x, a23.y}, c[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fma(a[i], c[jj], acc[i][jj]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int r = r0 + i, c = c0 + jj;
+        t[i][jj] = (r < b && c < b) ? Gall[(size_t)max(r, c) * ld + kold + min(r, c)] - acc[i][jj] : (r == c ? 1.0 : 0.0);
+      }
+    if (tx == ty) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = r0 + i;
+        if (r < b) {
+          const double cc = Gall[(size_t)r * ld + kold + r], d = t[i][i];
+          // the projected column must keep a safe fraction of its norm, otherwise G' is round-off
+          if (!(cc > 0.0) || !(d > 1e-10 * cc)) { badd = 1; dsc[r] = 0.0; cn[r] = 0.0; }
+          else { dsc[r] = MODE == 0 ? rsqrt(d) : 1.0; cn[r] = rsqrt(cc); }
+        } else {
+          dsc[r] = 1.0;
+          cn[r] = 0.0;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  double m0 = 0.0, m1 = 0.0;
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int r = r0 + i, c = c0 + jj;
+        if (r < b && c < b) t[i][jj] *= dsc[r] * dsc[c];
+        const double dev = fabs(t[i][jj] - (r == c ? 1.0 : 0.0));
+        m1 = (dev == dev) ? fmax(m1, dev) : 1.0e300;
+        if (MODE == 1) W1[(size_t)r * bp + c] = t[i][jj] - (r == c ? 1.0 : 0.0);  // E
+      }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d0[i] = t[i][i];
+  }
+  for (int e = tid; e < kold * bp; e += nt) {
+    const int j = e % bp;
+    const double h = fabs(Hs[e]) * cn[j];
+    m0 = (h == h) ? fmax(m0, h) : 1.0e300;
+  }
+  m0 = block_reduce_max(m0, red);
+  m1 = block_reduce_max(m1, red);  // (ends with a barrier: E is complete in W1)
+
+  if (MODE == 0) {
+    chol_inv_tile_body(T, active, tx, ty, t, d0, W1, buf, rinv_s, &bad);
+    if (bad || badd) {
+      if (tid == 0) { metrics[0] = m0; metrics[1] = m1; metrics[2] = badd ? 1.0 : 0.0; metrics[3] = bad ? 1.0 : 0.0; }
+      return;  // uniform; Z is not used by the caller in this case
+    }
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int r = r0 + i, c = c0 + jj;
+          t[i][jj] = (r <= c && r < b && c < b) ? t[i][jj] * dsc[r] : 0.0;
+        }
+    }
+  } else {
+    if (active) {
+      double acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) acc[i][jj] = 0.0;
+      for (int l = 0; l < bp; ++l) {  // E^2 (E symmetric: column l of E = row l)
+        const double2 a01 = *reinterpret_cast<const double2*>(W1 + (size_t)l * bp + r0);
+        const double2 a23 = *reinterpret_cast<const double2*>(W1 + (size_t)l * bp + r0 + 2);
+        const double2 b01 = *reinterpret_cast<const double2*>(W1 + (size_t)l * bp + c0);
+        const double2 b23 = *reinterpret_cast<const double2*>(W1 + (size_t)l * bp + c0 + 2);
+        const double a[4] = {a01.x, a01.y, a23.x, a23.y}, c[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fma(a[i], c[jj], acc[i][jj]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int r = r0 + i, c = c0 + jj;
+          const double E = t[i][jj] - (r == c ? 1.0 : 0.0);
+          t[i][jj] = (r < b && c < b) ? (r == c ? 1.0 : 0.0) - 0.5 * E + 0.375 * acc[i][jj] : 0.0;
+        }
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int r = r0 + i, c = c0 + jj;
+        W2[(size_t)r * bp + c] = t[i][jj];
+        if (r < b && c < b) Z[(size_t)c * ld + kold + r] = t[i][jj];
+      }
+  }
+  __syncthreads();
+  // rows 0..kold of Z: -H * Tm, 4 x 4 register blocks over all threads
+  const int ngrp = nt / T;  // row groups of 4 rows
+  for (int i0 = 4 * (tid / T); i0 < kold; i0 += 4 * ngrp) {
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) acc[i][jj] = 0.0;
+    const int lmax = MODE == 0 ? min(bp, c0 + 4) : bp;  // Tm upper triangular in MODE 0
+    for (int l = 0; l < lmax; ++l) {
+      const double2 w01 = *reinterpret_cast<const double2*>(W2 + (size_t)l * bp + c0);
+      const double2 w23 = *reinterpret_cast<const double2*>(W2 + (size_t)l * bp + c0 + 2);
+      const double w[4] = {w01.x, w01.y, w23.x, w23.y};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double h = (i0 + i < kold) ? Hs[(size_t)(i0 + i) * bp + l] : 0.0;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fma(h, w[jj], acc[i][jj]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj)
+        if (i0 + i < kold && c0 + jj < b) Z[(size_t)(c0 + jj) * ld + i0 + i] = -acc[i][jj];
+  }
+  if (tid == 0) {
+    metrics[0] = m0;
+    metrics[1] = m1;
+    metrics[2] = (badd || (MODE == 1 && !(m1 < 1e-5))) ? 1.0 : 0.0;
+    metrics[3] = 0.0;
+  }
+}
+
 }  // namespace
 
 void pip_prepare(cudaStream_t s, int k, int b, const double* Gall, const double* P, double* Gs, double* D,
@@ -781,6 +981,30 @@ void pip_finish(cudaStream_t s, int k, int b, const double* Tinv, const double* 
   pip_finish_kernel<<<std::max(1, std::min(64, (b * b + 255) / 256)), 256, 0, s>>>(k, b, Tinv, D, Tm, M);
   CK_LAUNCH();
   ++g_kernel_launches;
+}
+
+bool pip_small(cudaStream_t s, int mode, int kold, int b, const double* Gall, double* Z, double* metrics) {
+  static const bool off = [] { const char* e = std::getenv("DAV_PIP_FUSED"); return e && std::atoi(e) == 0; }();
+  if (off || b < 1 || b > 128 || kold < 1) return false;
+  const int T = (b + 3) / 4, bp = 4 * T;
+  const size_t bytes = ((size_t)kold * bp + 2 * (size_t)bp * bp + 5 * (size_t)bp) * sizeof(double);
+  const int max_smem = device_max_smem_optin();
+  if (bytes > (size_t)max_smem - 1024) return false;
+  const int nt = std::min(1024, std::max(256, (T * T + 31) / 32 * 32));
+#define DAV_PIP_LAUNCH(MODE_, NTMAX_)                                                      \
+  do {                                                                                     \
+    ensure_dyn_smem(pip_small_kernel<MODE_, NTMAX_>, max_smem - 1024);                     \
+    pip_small_kernel<MODE_, NTMAX_><<<1, nt, bytes, s>>>(kold, b, Gall, Z, metrics);       \
+  } while (0)
+  if (mode == 0) {
+    if (nt <= 256) DAV_PIP_LAUNCH(0, 256); else DAV_PIP_LAUNCH(0, 1024);
+  } else {
+    if (nt <= 256) DAV_PIP_LAUNCH(1, 256); else DAV_PIP_LAUNCH(1, 1024);
+  }
+#undef DAV_PIP_LAUNCH
+  CK_LAUNCH();
+  ++g_kernel_launches;
+  return true;
 }
 
 void jacobi_eigh(cudaStream_t s, int k, double* S, double* Y, double* w, double* scratch, int* status,

@@ -52,6 +52,8 @@ dav_solver::dav_solver(int device_, int rank, int world, const void* id128) : de
               prop.minor);
   comm.init(rank, world, id128);
   CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&pip_flags_ev, cudaEventDisableTiming));
+  CK(cudaMallocHost((void**)&pip_flags_host, 8 * sizeof(double)));
   std::memset(&stats, 0, sizeof(stats));
 }
 
@@ -64,6 +66,8 @@ dav_solver::~dav_solver() {
     if (mat[w].ftab) free_tables_destroy(mat[w].ftab);
   }
   for (cudaEvent_t ev : ev_pool) cudaEventDestroy(ev);
+  if (pip_flags_ev) cudaEventDestroy(pip_flags_ev);
+  if (pip_flags_host) cudaFreeHost(pip_flags_host);
   if (pinned_out) cudaFreeHost(pinned_out);
   if (stream) cudaStreamDestroy(stream);
 }
@@ -494,9 +498,9 @@ void dav_solver::rayleigh_ritz(int k, bool gev) {
 
 // C(M x N) = sum over ranks of A(:, 0:M)^T B(:, 0:N) (local rows of two n x . blocks), stored per `out`
 void dav_solver::tn_reduce(int M, int N, const double* A, const double* B, dav::DevBuf<double>& ws,
-                           const dav::ReduceOut& out) {
+                           const dav::ReduceOut& out, const dav::GemmSplit* split) {
   int parts = 0;
-  gemm(stream, true, M, N, nl, 1.0, A, ldv, B, ldv, 0.0, nullptr, 0, ws.p, ws.n, &parts);
+  gemm(stream, true, M, N, nl, 1.0, A, ldv, B, ldv, 0.0, nullptr, 0, ws.p, ws.n, &parts, split);
   const int sp = comm.active() ? begin_span(SPAN_COMM) : -1;
   if (parts == 0) {  // a rank without rows contributes zeros
     fill_zero(stream, ws.p, (size_t)M * N);
@@ -589,33 +593,54 @@ bool dav_solver::orthonormalize_block_pip(int b, int kold) {
   const int sp = begin_span(SPAN_ORTH);
   double* Vnew = V.p + (size_t)kold * ldv;
   auto small_ops = [&](int pass) {  // G.p = Gall (kb x b) -> Z.p = M (kb x b); metrics in small.p[4*pass ..]
+    if (pip_small(stream, pass, kold, b, G.p, Z.p, small.p + 4 * pass)) return;  // one kernel (b <= ~96)
     gemm(stream, true, b, b, kold, 1.0, G.p, kb, G.p, kb, 0.0, S1.p, b, nullptr, 0);  // P = H^T H
     pip_prepare(stream, kold, b, G.p, S1.p, S2.p, D.p, small.p + 4 * pass);
     chol_inv_upper(stream, b, S2.p, U.p, small.p + 4 * pass + 3, jscratch.p, jscratch.n);
     pip_finish(stream, kold, b, U.p, D.p, Tm.p, Z.p);
     gemm(stream, false, kold, b, b, -1.0, G.p, kb, Tm.p, b, 0.0, Z.p, kb, nullptr, 0);  // rows 0..k: -H Tm
   };
+  // [V | T] as ONE operand of the tall-skinny products (kold % 4 == 0: always, kold = 2L * 2^i)
+  const bool two_block = kold % 4 == 0;
+  const GemmSplit vt{T.p, ldv, kold};
   // pass 1: [V C]^T C in one product (split-K partials summed over K and over the ranks by one kernel),
   // C1 = [V C] M -> T
   tn_reduce(kb, b, V.p, Vnew, gemm_ws, dav::ReduceOut{0, G.p, kb, 0});
   small_ops(0);
   gemm(stream, false, nl, b, kb, 1.0, V.p, ldv, Z.p, kb, 0.0, T.p, ldv, nullptr, 0);
   // pass 2: H = V^T C1 and C1^T C1 into the rows 0..kold / kold.. of the same block
-  tn_reduce(kold, b, V.p, T.p, gemm_ws, dav::ReduceOut{0, G.p, kb, 0});
-  tn_reduce(b, b, T.p, T.p, gemm_ws2, dav::ReduceOut{0, G.p + kold, kb, 0});
+  if (two_block) {
+    tn_reduce(kb, b, V.p, T.p, gemm_ws, dav::ReduceOut{0, G.p, kb, 0}, &vt);
+  } else {
+    tn_reduce(kold, b, V.p, T.p, gemm_ws, dav::ReduceOut{0, G.p, kb, 0});
+    tn_reduce(b, b, T.p, T.p, gemm_ws2, dav::ReduceOut{0, G.p + kold, kb, 0});
+  }
   small_ops(1);
-  double h[8];
-  CK(cudaMemcpyAsync(h, small.p, sizeof(h), cudaMemcpyDeviceToHost, stream));
-  CK(cudaStreamSynchronize(stream));
-  // pass 1: pivots safe, Cholesky succeeded; pass 2 started from an almost orthonormal block
-  const bool ok = h[2] == 0.0 && h[3] == 0.0 && h[6] == 0.0 && h[7] == 0.0 && h[4] < 1e-6 && h[5] < 1e-6;
-  if (ok) {
-    // C2 = C1 * Tm - V * (H Tm) -> V(:, kold:)
+  // The flags of both passes are read while the GPU already runs the final update (and whatever the caller enqueues
+  // next): the update is only WRONG, never harmful, when the flags say so -- the caller then restores the block from
+  // C and takes the fallback path.
+  CK(cudaMemcpyAsync(pip_flags_host, small.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  CK(cudaEventRecord(pip_flags_ev, stream));
+  // C2 = C1 * Tm - V * (H Tm) = [V | C1] M -> V(:, kold:)
+  if (two_block) {
+    gemm(stream, false, nl, b, kb, 1.0, V.p, ldv, Z.p, kb, 0.0, Vnew, ldv, nullptr, 0, nullptr, &vt);
+  } else {
     gemm(stream, false, nl, b, b, 1.0, T.p, ldv, Z.p + kold, kb, 0.0, Vnew, ldv, nullptr, 0);
     gemm(stream, false, nl, b, kold, 1.0, V.p, ldv, Z.p, kb, 1.0, Vnew, ldv, nullptr, 0);
   }
   end_span(sp);
-  return ok;
+  return true;
+}
+
+// second half of orthonormalize_block_pip: waits for the flags (the stream keeps running) and judges them
+bool dav_solver::pip_confirm() {
+  CK(cudaEventSynchronize(pip_flags_ev));
+  // DAV_PIP_FORCE_REJECT=1 (tests): judge every fast pass as failed, so that the rebuild-from-C path runs
+  static const bool force_reject = [] { const char* e = std::getenv("DAV_PIP_FORCE_REJECT"); return e && std::atoi(e) != 0; }();
+  if (force_reject) return false;
+  const double* h = pip_flags_host;
+  // pass 1: pivots safe, Cholesky succeeded; pass 2 started from an almost orthonormal block
+  return h[2] == 0.0 && h[3] == 0.0 && h[6] == 0.0 && h[7] == 0.0 && h[4] < 1e-6 && h[5] < 1e-6;
 }
 
 int dav_solver::solve(int lowest, int method, int max_iterations, double tolerance, int max_dim_sub,
@@ -781,10 +806,21 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
       if (method == DAV_METHOD_GJD) gjd_correction(k, gev, tolerance);  // C <- GJD corrections
       double* Q = V.p + (size_t)k * ldv;
       copy_matrix(stream, nl, k, C.p, ldv, Q, ldv);                   // [V | C] contiguous
-      if (!orthonormalize_block_pip(k, k))                            // steps 6-7 (:210-213)
+      const bool pip = orthonormalize_block_pip(k, k);                // steps 6-7 (:210-213), enqueued
+      if (!pip) orthonormalize_block(Q, k, k, Q);
+      auto expand = [&]() {
+        apply_both(Q, k, AV.p + (size_t)k * ldv, gev ? BV.p + (size_t)k * ldv : nullptr);  // the block matvec(s)
+        for (int w = 0; w < (gev ? 2 : 1); ++w) project_new_block(w, k, k);
+      };
+      expand();
+      // the flags of the fast orthonormalisation arrive while the matvec runs; in the rare case that they reject it
+      // (rank-deficient or ill-conditioned block) the block is rebuilt from the corrections, which are still in C
+      if (pip && !pip_confirm()) {
+        stats.pip_fallbacks += 1;
+        copy_matrix(stream, nl, k, C.p, ldv, Q, ldv);
         orthonormalize_block(Q, k, k, Q);
-      apply_both(Q, k, AV.p + (size_t)k * ldv, gev ? BV.p + (size_t)k * ldv : nullptr);  // the block matvec(s)
-      for (int w = 0; w < (gev ? 2 : 1); ++w) project_new_block(w, k, k);
+        expand();
+      }
       k *= 2;
     } else {                                                          // collapse (:218)
       sp = begin_span(SPAN_ORTH);

@@ -51,6 +51,8 @@ struct dav_solver {
   double* pinned_out = nullptr;
   size_t pinned_out_n = 0;
   double* pinned(size_t count);
+  double* pip_flags_host = nullptr;  // page-locked landing zone of the orthonormalisation flags
+  cudaEvent_t pip_flags_ev = nullptr;
   std::vector<cudaEvent_t> ev_pool;
   struct Span { int a, b, kind; };
   std::vector<Span> spans;
@@ -92,10 +94,12 @@ struct dav_solver {
   void alloc_work(int lowest, int kcap_);
   void rayleigh_ritz(int k, bool gev);
   void orthonormalize_block(double* Cblk, int b, int kold, double* dest);
-  bool orthonormalize_block_pip(int b, int kold);
+  bool orthonormalize_block_pip(int b, int kold);  // enqueues the fast path; false = shape unsupported, nothing enqueued
+  bool pip_confirm();                              // true when the flags of the enqueued fast path accept it
   void gjd_correction(int k, bool gev, double outer_tolerance);
   void project_new_block(int which, int kold, int b);
-  void tn_reduce(int M, int N, const double* A, const double* B, dav::DevBuf<double>& ws, const dav::ReduceOut& out);
+  void tn_reduce(int M, int N, const double* A, const double* B, dav::DevBuf<double>& ws, const dav::ReduceOut& out,
+                 const dav::GemmSplit* split = nullptr);
   void full_projection(int which, int k);
   void allreduce(double* buf, size_t count);
   void allgather(const void* send, void* recv, size_t bytes_per_rank);

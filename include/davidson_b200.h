@@ -171,6 +171,7 @@ typedef struct {
   int collectives;          /* inter-GPU exchanges of the solve (own peer-memory kernels or NCCL calls) */
   int spans_dropped;        /* phase spans not timed because the event pool was exhausted (0: the *_ms are complete) */
   int peer_transport;       /* 1: the exchanges were the library's peer-memory kernels, 0: NCCL / single GPU */
+  int pip_fallbacks;        /* expansion blocks whose fast orthonormalisation was rejected and redone by the SVQB loop */
 } dav_stats_t;
 int dav_get_stats(dav_solver_t* h, dav_stats_t* out);
 
@@ -199,6 +200,12 @@ int dav_debug_matvec_rect(int device, int64_t m, int64_t k, int b, double* max_a
  * symmetric positive definite, column-major, upper triangle read; t <- R^-1 with g = R^T R (upper triangular, zeros
  * below); *flag = 1.0 when a pivot was not safely positive (t is then undefined); *ms (may be NULL) = kernel time. */
 int dav_debug_chol_inv(int b, const double* g, double* t, double* flag, float* ms);
+
+/* Test entry of the fused small-matrix kernel of the block orthonormalisation (csrc/smalldense.cu pip_small_kernel; host
+ * pointers): gall = (kold + b) x b column-major, rows 0..kold = H = V^T C, rows kold.. = C^T C; z <- [-H Tm; Tm] with
+ * Tm^T (C^T C - H^T H) Tm = I; mode 0 = first pass (scaled Cholesky), 1 = second pass (series); metrics[4] as in the
+ * kernel; *launched = 0 when the shape does not fit the fused kernel (the solver then uses the separate kernels). */
+int dav_debug_pip_small(int mode, int kold, int b, const double* gall, double* z, double* metrics, int* launched);
 
 /* Timing entry of the tall-skinny products around the block matvec (csrc/dgemm.cu), operands generated on the
  * device: C (m x n) = op(A) * B with op(A) m x k, B k x n; transA 'T' = the projection shape (k = local rows, split-K).

@@ -129,6 +129,78 @@ def test_wide_third_expansion_block_lowest_32():
     _check_against_oracle(A, None, ev, vec, r, 1e-9)
 
 
+# ---------------------------------------------------------------- fused orthonormalisation: passes and the reject path
+@pytest.mark.parametrize("kold,b", [(6, 6), (32, 32), (64, 64), (40, 40), (80, 80), (20, 7), (128, 64), (96, 96)])
+def test_fused_pip_passes_match_the_separate_kernels(kold, b):
+    """dav_debug_pip_small: Z = [-H Tm; Tm] of one BCGS-PIP pass from the fused kernel (mode 0: scaled Cholesky, mode 1:
+    series of (I + E)^-1/2) against numpy: Tm^T (C^T C - H^T H) Tm = I and the top block = -H Tm."""
+    rng = np.random.default_rng(kold * 131 + b)
+    n = 4 * (kold + b) + 50
+    V, _ = np.linalg.qr(rng.standard_normal((n, kold)))
+    for mode in (0, 1):
+        C0 = rng.standard_normal((n, b))
+        if mode == 1:  # second pass: already orthonormal to ~1e-9
+            C0 = C0 - V @ (V.T @ C0)
+            C0, _ = np.linalg.qr(C0)
+            C0 = C0 + 1e-9 * rng.standard_normal((n, b)) + 1e-9 * V @ rng.standard_normal((kold, b))
+        H = V.T @ C0
+        Gall = np.asfortranarray(np.vstack([H, C0.T @ C0]))
+        Z = np.zeros((kold + b, b), order="F")
+        met = np.zeros(4)
+        ok = C.c_int(0)
+        check(lib().dav_debug_pip_small(C.c_int(mode), C.c_int(kold), C.c_int(b), dp(Gall), dp(Z), dp(met), C.byref(ok)))
+        assert ok.value == 1, (mode, kold, b)
+        assert met[2] == 0.0 and met[3] == 0.0, met
+        Tm = Z[kold:]
+        Gp = C0.T @ C0 - H.T @ H
+        assert np.abs(Tm.T @ Gp @ Tm - np.eye(b)).max() < 1e-10 * max(1.0, np.linalg.cond(Gp))
+        assert np.abs(Z[:kold] + H @ Tm).max() <= 1e-12 * max(1.0, np.abs(H).max() * np.abs(Tm).max() * b)
+        Q = C0 @ Tm + V @ Z[:kold]
+        assert np.abs(V.T @ Q).max() < 1e-8 and np.abs(Q.T @ Q - np.eye(b)).max() < 1e-8
+        assert abs(met[0] - (np.abs(H) / np.sqrt(np.diag(C0.T @ C0))).max()) <= 1e-12 + 1e-9 * met[0]
+
+
+def test_fused_pip_flags_a_dependent_block():
+    rng = np.random.default_rng(3)
+    n, kold, b = 400, 16, 16
+    V, _ = np.linalg.qr(rng.standard_normal((n, kold)))
+    C0 = rng.standard_normal((n, b))
+    C0[:, 5] = V[:, 2] * 3.0  # inside span(V): G' has a round-off diagonal entry
+    H = V.T @ C0
+    Gall = np.asfortranarray(np.vstack([H, C0.T @ C0]))
+    Z = np.zeros((kold + b, b), order="F")
+    met = np.zeros(4)
+    ok = C.c_int(0)
+    check(lib().dav_debug_pip_small(C.c_int(0), C.c_int(kold), C.c_int(b), dp(Gall), dp(Z), dp(met), C.byref(ok)))
+    assert ok.value == 1 and met[2] == 1.0
+    # second pass input that is not close to orthonormal: |E| >= 1e-5 raises the flag
+    C1, _ = np.linalg.qr(C0 - V @ (V.T @ C0) + rng.standard_normal((n, b)))
+    C1 = C1 * 1.001
+    Gall = np.asfortranarray(np.vstack([V.T @ C1, C1.T @ C1]))
+    check(lib().dav_debug_pip_small(C.c_int(1), C.c_int(kold), C.c_int(b), dp(Gall), dp(Z), dp(met), C.byref(ok)))
+    assert ok.value == 1 and met[2] == 1.0
+
+
+def test_rejected_fast_orthonormalisation_is_rebuilt_from_the_corrections():
+    """DAV_PIP_FORCE_REJECT=1: every fast pass is judged as failed after the matvec has already been enqueued on its
+    output; the block must be rebuilt from the corrections by the SVQB loop with the same results."""
+    n, L = 3000, 10
+    A = orc.generate_diagonal_dominant(n, 5e-2, None, 0)
+    r = orc.generalized_eigensolver(A, L, "DPR", 1000, 1e-8, 100)
+    code = ("import numpy as np, json, sys; sys.path.insert(0, %r)\n"
+            "import fortran_davidson_b200 as fd\n"
+            "s = fd.DavidsonSolver(); s.generate_diagonal_dominant(0, %d, 5e-2, None, 0)\n"
+            "ev, vec, it = s.solve(%d, 'DPR', 1000, 1e-8, 100); st = s.stats()\n"
+            "print(json.dumps({'ev': ev.tolist(), 'it': it, 'fb': st.pip_fallbacks}))" % (ROOT, n, L))
+    env = dict(os.environ, DAV_PIP_FORCE_REJECT="1")
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    import json
+    d = json.loads(p.stdout.strip().splitlines()[-1])
+    assert d["fb"] >= 3 and abs(d["it"] - r.iters) <= 1
+    assert np.abs(np.array(d["ev"]) - r.eigenvalues).max() / np.abs(r.eigenvalues).max() < EV_RTOL
+
+
 # ---------------------------------------------------------------- GJD: iteration counts equal on >= 4 iterations
 @pytest.mark.parametrize("gev", [False, True])
 def test_gjd_iteration_count_equal_on_longer_runs(gev):
