@@ -337,6 +337,163 @@ __global__ void __launch_bounds__(128 * KG) gemm_dmma_kernel(int64_t M, int64_t 
   }
 }
 
+// ---- r02: residuals + DPR corrections in ONE pass over the stored products (davidson.f90:163-170 via AV, (BV|V);
+// :688-696; free :401-410, :484).  Was: GEMM AV*Y -> R, GEMM (BV|V)*Y -> C, residual_dpr_kernel (reads both, writes
+// both) + stage 2 of the norms.  Here both products share the Y fragments of one k-loop (two accumulator sets per
+// warp), and the epilogue forms r = AV y - theta (BV|V) y, the correction r / (theta dB_i - dA_i) (or, for GJD, the
+// B-product (BV|V) y itself) and the column sums of r^2 of the warp's 32 rows (three shuffle stages over the 8 row
+// lanes), written per (column, CTA row block) and summed in a fixed order by norm_partials_kernel.
+template <int WNS>
+__global__ void __launch_bounds__(128) resid_dmma_kernel(int64_t M, int64_t N, int64_t K,
+                                                        const double* __restrict__ A1, const double* __restrict__ A2,
+                                                        int64_t lda, const double* __restrict__ Y, int64_t ldy,
+                                                        const double* __restrict__ theta,
+                                                        const double* __restrict__ dA, const double* __restrict__ dB,
+                                                        int write_correction, double* __restrict__ R, int64_t ldr,
+                                                        double* __restrict__ C, int64_t ldc,
+                                                        double* __restrict__ partial, int P) {
+  constexpr int WMS = 4 / WNS;
+  constexpr int UNR = 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp % WMS, wn = warp / WMS;
+  const int64_t m0 = (int64_t)blockIdx.x * (32 * WMS) + wm * 32;
+  const int64_t n0 = (int64_t)blockIdx.y * (32 * WNS) + wn * 32;
+  if (n0 >= N) return;  // warp-uniform (no barrier in this kernel)
+  if (m0 >= M) {        // a warp below the last row still owns a slot of the norm partials
+    if (g == 0) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int64_t n = n0 + 8 * (q >> 1) + 2 * t + (q & 1);
+        if (n < N) partial[(size_t)n * P + (blockIdx.x * WMS + wm)] = 0.0;
+      }
+    }
+    return;
+  }
+  double accA[4][4][2], accB[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) accA[i][j][0] = accA[i][j][1] = accB[i][j][0] = accB[i][j][1] = 0.0;
+  int64_t aoff[4];
+  const double* bp[4];
+  bool mi[4], nj[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    aoff[i] = min(m0 + 8 * i + g, M - 1) + (int64_t)t * lda;
+    bp[i] = Y + min(n0 + 8 * i + g, N - 1) * ldy + t;
+    mi[i] = m0 + 8 * i < M;
+    nj[i] = n0 + 8 * i < N;
+  }
+  int64_t kk = 0;
+  for (; kk + 4 * UNR <= K; kk += 4 * UNR) {
+    double a1[UNR][4], a2[UNR][4], b[UNR][4];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        a1[u][i] = A1[aoff[i] + (kk + 4 * u) * lda];
+        a2[u][i] = A2[aoff[i] + (kk + 4 * u) * lda];
+        b[u][i] = bp[i][kk + 4 * u];
+      }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (!mi[i]) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (!nj[j]) continue;
+          asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+              : "+d"(accA[i][j][0]), "+d"(accA[i][j][1])
+              : "d"(a1[u][i]), "d"(b[u][j]));
+          asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+              : "+d"(accB[i][j][0]), "+d"(accB[i][j][1])
+              : "d"(a2[u][i]), "d"(b[u][j]));
+        }
+      }
+  }
+  for (; kk < K; kk += 4) {
+    const bool kin = kk + t < K;
+    double a1[4], a2[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      a1[i] = kin ? A1[aoff[i] + kk * lda] : 0.0;
+      a2[i] = kin ? A2[aoff[i] + kk * lda] : 0.0;
+      b[i] = kin ? bp[i][kk] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (!mi[i]) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!nj[j]) continue;
+        asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+            : "+d"(accA[i][j][0]), "+d"(accA[i][j][1])
+            : "d"(a1[i]), "d"(b[j]));
+        asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+            : "+d"(accB[i][j][0]), "+d"(accB[i][j][1])
+            : "d"(a2[i]), "d"(b[j]));
+      }
+    }
+  }
+  // ---- epilogue
+  double dAi[4], dBi[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = min(m0 + 8 * i + g, M - 1);
+    dAi[i] = dA[m];
+    dBi[i] = dB ? dB[m] : 1.0;
+  }
+  const int pid = blockIdx.x * WMS + wm;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (!nj[j]) continue;  // warp-uniform
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int64_t n = n0 + 8 * j + 2 * t + c;
+      const bool nin = n < N;
+      const double th = theta[nin ? n : N - 1];
+      double ssq = 0.0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t m = m0 + 8 * i + g;
+        if (m < M && nin) {
+          const double r = accA[i][j][c] - th * accB[i][j][c];
+          R[m + n * ldr] = r;
+          ssq = fma(r, r, ssq);
+          // davidson.f90:691,693 / :484, unguarded
+          C[m + n * ldc] = write_correction ? r / (th * dBi[i] - dAi[i]) : accB[i][j][c];
+        }
+      }
+      // sum over the 8 row lanes (same t)
+      ssq += __shfl_xor_sync(0xffffffffu, ssq, 4);
+      ssq += __shfl_xor_sync(0xffffffffu, ssq, 8);
+      ssq += __shfl_xor_sync(0xffffffffu, ssq, 16);
+      if (g == 0 && nin) partial[(size_t)n * P + pid] = ssq;
+    }
+  }
+}
+
+// out[j] = sum of partial[j * P + 0 .. P) in a fixed order: one warp per column, lanes strided, butterfly at the end
+__global__ void __launch_bounds__(256) norm_partials_kernel(int N, int P, const double* __restrict__ partial,
+                                                           double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= N) return;
+  double s0 = 0.0, s1 = 0.0;
+  int p = lane;
+  for (; p + 32 < P; p += 64) {
+    s0 += partial[(size_t)j * P + p];
+    s1 += partial[(size_t)j * P + p + 32];
+  }
+  if (p < P) s0 += partial[(size_t)j * P + p];
+  double s = s0 + s1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[j] = s;
+}
+
 // Sums the split-K partials in a fixed order (bit-reproducible).  A CTA owns 64 consecutive output elements; its 4
 // thread groups each add every 4th partial (coalesced 512-byte rows of the workspace) and the 4 group sums are
 // combined in shared memory in group order.
@@ -377,6 +534,36 @@ int env_or(const char* name, int dflt) {
   return e ? std::atoi(e) : dflt;
 }
 }  // namespace
+
+size_t residual_fused_partials(int64_t nl, int nc) {
+  return (size_t)std::max(nc, 1) * (size_t)(ceil_div(std::max<int64_t>(nl, 1), 32) + 4);
+}
+
+void residual_fused(cudaStream_t s, int64_t nl, int nc, int k, const double* AV, const double* BV, int64_t ldv,
+                    const double* Y, int64_t ldy, const double* theta, const double* dA, const double* dB,
+                    bool write_correction, double* R, int64_t ldr, double* C, int64_t ldc, double* partial,
+                    double* n2out) {
+  if (nc <= 0) return;
+  if (nl <= 0) {  // a rank without rows contributes zero norms
+    CK(cudaMemsetAsync(n2out, 0, (size_t)nc * sizeof(double), s));
+    return;
+  }
+  const int wns = nc <= 32 ? 1 : 2;
+  const int bm = 32 * (4 / wns), bn = 32 * wns;
+  const dim3 grid((unsigned)ceil_div(nl, bm), (unsigned)ceil_div(nc, bn));
+  const int P = (int)grid.x * (4 / wns);
+  if (wns == 1)
+    resid_dmma_kernel<1><<<grid, 128, 0, s>>>(nl, nc, k, AV, BV, ldv, Y, ldy, theta, dA, dB, write_correction ? 1 : 0, R,
+                                              ldr, C, ldc, partial, P);
+  else
+    resid_dmma_kernel<2><<<grid, 128, 0, s>>>(nl, nc, k, AV, BV, ldv, Y, ldy, theta, dA, dB, write_correction ? 1 : 0, R,
+                                              ldr, C, ldc, partial, P);
+  CK_LAUNCH();
+  ++g_kernel_launches;
+  norm_partials_kernel<<<(nc + 7) / 8, 256, 0, s>>>(nc, P, partial, n2out);
+  CK_LAUNCH();
+  ++g_kernel_launches;
+}
 
 void gemm(cudaStream_t s, bool transA, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
           const double* B, int64_t ldb, double beta, double* C, int64_t ldc, double* ws, size_t ws_doubles,

@@ -26,6 +26,16 @@ void gemm(cudaStream_t s, bool transA, int64_t M, int64_t N, int64_t K, double a
           int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, double* ws,
           size_t ws_doubles, int* partials_out = nullptr, const GemmSplit* split = nullptr);
 
+// Residuals + corrections of nc Ritz pairs in one pass (davidson.f90:163-170 via the stored products, :688-696):
+//   R(:, j) = AV y_j - theta_j (BV|V) y_j;   C(:, j) = R(:, j) / (theta_j dB - dA)  (write_correction; dB == nullptr
+//   -> 1), else C(:, j) = (BV|V) y_j (the GJD solver wants the B-product);   n2out[j] = sum of R(:, j)^2.
+// AV, BV: nl x k (ldv); Y: k x nc (ldy).  partial: >= residual_fused_partials(nl, nc) doubles.
+size_t residual_fused_partials(int64_t nl, int nc);
+void residual_fused(cudaStream_t s, int64_t nl, int nc, int k, const double* AV, const double* BV, int64_t ldv,
+                    const double* Y, int64_t ldy, const double* theta, const double* dA, const double* dB,
+                    bool write_correction, double* R, int64_t ldr, double* C, int64_t ldc, double* partial,
+                    double* n2out);
+
 // ---- matvec_dmma.cu : the hot kernel.  W(M x b) = A(M x K, lda) * X(K x b)  ---------------------
 // TMA (2D tensor map, 128B swizzle) -> mbarrier pipeline -> FP64 DMMA, persistent stream-K grid.
 struct MatvecPlan;  // opaque: tensor map + workspace for one resident matrix

@@ -435,7 +435,7 @@ void dav_solver::alloc_work(int lowest, int kcap_) {
   Z.alloc(kk);
   theta.alloc(kcap); sv.alloc(kcap); D.alloc(kcap); norms2.alloc(kcap);
   jscratch.alloc(sym_eigh_scratch_doubles(kcap));
-  partial.alloc((size_t)kcap * 64);
+  partial.alloc(std::max((size_t)kcap * 64, residual_fused_partials(nl, kcap)));
   gemm_ws.alloc(std::max<size_t>(kk * 64, (size_t)1 << 22));
   gemm_ws2.alloc(std::max<size_t>(kk * 16, (size_t)1 << 20));
   small.alloc(16);
@@ -733,11 +733,18 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
     // then tests the first L (davidson.f90:163-178); here the first L columns come first and the other k-L (needed
     // only for the corrections of a NEXT iteration) are skipped when the test passes or the iteration budget ends.
     auto residual_cols = [&](int c0, int nc) {
-      gemm(stream, false, nl, nc, k, 1.0, AV.p, ldv, Y.p + (size_t)c0 * k, k, 0.0, R.p + (size_t)c0 * ldv, ldv, nullptr, 0);
-      gemm(stream, false, nl, nc, k, 1.0, gev ? BV.p : V.p, ldv, Y.p + (size_t)c0 * k, k, 0.0, C.p + (size_t)c0 * ldv,
-           ldv, nullptr, 0);
-      residual_dpr(stream, nl, nc, R.p + (size_t)c0 * ldv, ldv, C.p + (size_t)c0 * ldv, ldv, theta.p + c0,
-                   mat[0].diag.p, gev ? mat[1].diag.p : nullptr, method == DAV_METHOD_DPR, partial.p, norms2.p + c0);
+      static const bool unfused = [] { const char* e = std::getenv("DAV_RESIDUAL_FUSED"); return e && std::atoi(e) == 0; }();
+      if (!unfused) {
+        residual_fused(stream, nl, nc, k, AV.p, gev ? BV.p : V.p, ldv, Y.p + (size_t)c0 * k, k, theta.p + c0,
+                       mat[0].diag.p, gev ? mat[1].diag.p : nullptr, method == DAV_METHOD_DPR,
+                       R.p + (size_t)c0 * ldv, ldv, C.p + (size_t)c0 * ldv, ldv, partial.p, norms2.p + c0);
+      } else {
+        gemm(stream, false, nl, nc, k, 1.0, AV.p, ldv, Y.p + (size_t)c0 * k, k, 0.0, R.p + (size_t)c0 * ldv, ldv, nullptr, 0);
+        gemm(stream, false, nl, nc, k, 1.0, gev ? BV.p : V.p, ldv, Y.p + (size_t)c0 * k, k, 0.0, C.p + (size_t)c0 * ldv,
+             ldv, nullptr, 0);
+        residual_dpr(stream, nl, nc, R.p + (size_t)c0 * ldv, ldv, C.p + (size_t)c0 * ldv, ldv, theta.p + c0,
+                     mat[0].diag.p, gev ? mat[1].diag.p : nullptr, method == DAV_METHOD_DPR, partial.p, norms2.p + c0);
+      }
       if (c0 == 0) allreduce(norms2.p, nc);  // only the first L norms are tested (davidson.f90:173-178)
     };
     residual_cols(0, L);

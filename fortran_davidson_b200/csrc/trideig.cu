@@ -287,8 +287,8 @@ __device__ __forceinline__ double allreduce16(double x) {
   return x;
 }
 
-template <int TS>
-__global__ void __launch_bounds__(256) tridiag_reg_kernel(int k, const double* __restrict__ S_in,
+template <int TSR, int TS>  // tile = TSR rows x TS columns; 16 TS / TSR x 16 threads
+__global__ void __launch_bounds__(256 * TS / TSR) tridiag_reg_kernel(int k, const double* __restrict__ S_in,
                                                           double* __restrict__ Sfull, double* __restrict__ Vh,
                                                           double* __restrict__ tau, double* __restrict__ d,
                                                           double* __restrict__ e, double* __restrict__ scal) {
@@ -297,16 +297,16 @@ __global__ void __launch_bounds__(256) tridiag_reg_kernel(int k, const double* _
   __shared__ __align__(16) double vb[KP];    // reflector j: 0 for rows <= j, 1 at row j+1
   __shared__ __align__(16) double pb[KP];    // p = tau S v, exactly 0 on dead rows
   __shared__ double tjb;                     // tau of reflector j
-  __shared__ double red[8];
+  __shared__ double red[8 * TS / TSR];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, warp = tid >> 5;
   // rows of a tile are contiguous (TS ty ..); its columns are the pairs 2 tx, 2 tx + 1 of every 32-column group, so
   // that the 16 lanes of a half warp read 256 contiguous bytes of v / p with each 16-byte load (conflict-free)
-  const int r0 = ty * TS, c0 = 2 * tx;
+  const int r0 = ty * TSR, c0 = 2 * tx;
   auto col = [&](int q) { return c0 + 32 * (q >> 1) + (q & 1); };
-  double t[TS][TS];
+  double t[TSR][TS];
   double mx = 0.0;
 #pragma unroll
-  for (int i = 0; i < TS; ++i)
+  for (int i = 0; i < TSR; ++i)
 #pragma unroll
     for (int jj = 0; jj < TS; ++jj) {
       const int a = r0 + i, c = col(jj);
@@ -322,19 +322,19 @@ __global__ void __launch_bounds__(256) tridiag_reg_kernel(int k, const double* _
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((tid & 31) == 0) red[warp] = mx;
-  for (int i = tid; i < KP; i += 256) pb[i] = 0.0;
+  for (int i = tid; i < KP; i += blockDim.x) pb[i] = 0.0;
 
   // The warp that owns row jn builds reflector jn from it: v -> vb (and Vh), tau -> tjb (and tau[]), d, e.  The
   // step loop keeps its code small on purpose (one SM's instruction cache serves 8 warps in lock step): the row is
   // picked with a switch on jn % TS, and everyone else only ever loads finished vectors.
   auto publish = [&](int jn) {
-    if ((ty >> 1) != ((jn / TS) >> 1)) return;  // warp-uniform: the shuffles below need the whole warp
-    const bool own = ty == jn / TS;
+    if ((ty >> 1) != ((jn / TSR) >> 1)) return;  // warp-uniform: the shuffles below need the whole warp
+    const bool own = ty == jn / TSR;
     double x[TS];
-    switch (jn % TS) {
+    switch (jn % TSR) {
 #define TRI_ROW(I_)                                   \
   case I_:                                            \
-    if constexpr (I_ < TS) {                          \
+    if constexpr (I_ < TSR) {                         \
       _Pragma("unroll") for (int jj = 0; jj < TS; ++jj) x[jj] = t[I_][jj]; \
     }                                                 \
     break;
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(256) tridiag_reg_kernel(int k, const double* _
   __syncthreads();
   if (tid == 0) {
     double m = 0.0;
-    for (int i = 0; i < 8; ++i) m = fmax(m, red[i]);
+    for (int i = 0; i < 8 * TS / TSR; ++i) m = fmax(m, red[i]);
     scal[0] = m;  // max |S|
   }
 
@@ -404,34 +404,37 @@ __global__ void __launch_bounds__(256) tridiag_reg_kernel(int k, const double* _
 #endif
   for (int j = 0; j + 2 < k; ++j) {
     const double tj = tjb;
-    const int last_row = ((ty | 1) + 1) * TS - 1;  // last row of this warp
+    const int last_row = ((ty | 1) + 1) * TSR - 1;  // last row of this warp
     const bool warp_live = last_row > j;           // some row of this warp is still in the trailing matrix
-    const bool tile_live = r0 + TS - 1 > j;  // (the interleaved columns of a tile stay live until the last steps)
-    double vc[TS], vr[TS];
+    const bool tile_live = r0 + TSR - 1 > j;  // (the interleaved columns of a tile stay live until the last steps)
+    double vc[TS], vr[TSR];
     if (tj != 0.0 && warp_live) {  // uniform per warp
 #pragma unroll
       for (int q = 0; q < TS; q += 2) {
         const double2 a = *reinterpret_cast<const double2*>(vb + col(q));
-        const double2 b = *reinterpret_cast<const double2*>(vb + r0 + q);
         vc[q] = a.x; vc[q + 1] = a.y;
+      }
+#pragma unroll
+      for (int q = 0; q < TSR; q += 2) {
+        const double2 b = *reinterpret_cast<const double2*>(vb + r0 + q);
         vr[q] = b.x; vr[q + 1] = b.y;
       }
       // ---- p = tau S v: row sums of my tile, reduce-scatter over the 16 tiles of the row
-      double pt[TS];
+      double pt[TSR];
 #pragma unroll
-      for (int i = 0; i < TS; ++i) pt[i] = 0.0;
+      for (int i = 0; i < TSR; ++i) pt[i] = 0.0;
       if (tile_live) {
 #pragma unroll
-        for (int i = 0; i < TS; ++i)
+        for (int i = 0; i < TSR; ++i)
 #pragma unroll
           for (int jj = 0; jj < TS; ++jj) pt[i] = fma(t[i][jj], vc[jj], pt[i]);
       }
       TRI_A(0)
-      const int idx = reduce_scatter16<TS>(pt, tx);
-      constexpr int WMASK = TS == 8 ? 1 : (TS == 4 ? 3 : 7);
+      const int idx = reduce_scatter16<TSR>(pt, tx);
+      constexpr int WMASK = TSR == 8 ? 1 : (TSR == 4 ? 3 : 7);
       if ((tx & WMASK) == 0) pb[r0 + idx] = (r0 + idx > j) ? pt[0] * tj : 0.0;
     } else if (tj != 0.0 && last_row == j) {
-      if (tx < TS) pb[r0 + tx] = 0.0;  // this warp's rows just died: p stays exactly 0 there from now on
+      if (tx < TSR) pb[r0 + tx] = 0.0;  // this warp's rows just died: p stays exactly 0 there from now on
     }
     TRI_A(1)
     TRI_B(3)
@@ -439,13 +442,16 @@ __global__ void __launch_bounds__(256) tridiag_reg_kernel(int k, const double* _
     TRI_A(2)
     TRI_B(3)
     if (tj != 0.0 && warp_live) {
-      double pc[TS], pr[TS];
+      double pc[TS], pr[TSR];
       double pvp = 0.0;
 #pragma unroll
       for (int q = 0; q < TS; q += 2) {
         const double2 a = *reinterpret_cast<const double2*>(pb + col(q));
-        const double2 b = *reinterpret_cast<const double2*>(pb + r0 + q);
         pc[q] = a.x; pc[q + 1] = a.y;
+      }
+#pragma unroll
+      for (int q = 0; q < TSR; q += 2) {
+        const double2 b = *reinterpret_cast<const double2*>(pb + r0 + q);
         pr[q] = b.x; pr[q + 1] = b.y;
       }
 #pragma unroll
@@ -456,12 +462,11 @@ __global__ void __launch_bounds__(256) tridiag_reg_kernel(int k, const double* _
       if (tile_live) {
         // w = p + K v is 0 wherever v and p are (dead rows / columns): those entries are never touched again
 #pragma unroll
-        for (int q = 0; q < TS; ++q) {
-          pc[q] = fma(K, vc[q], pc[q]);
-          pr[q] = fma(K, vr[q], pr[q]);
-        }
+        for (int q = 0; q < TS; ++q) pc[q] = fma(K, vc[q], pc[q]);
 #pragma unroll
-        for (int i = 0; i < TS; ++i)
+        for (int q = 0; q < TSR; ++q) pr[q] = fma(K, vr[q], pr[q]);
+#pragma unroll
+        for (int i = 0; i < TSR; ++i)
 #pragma unroll
           for (int jj = 0; jj < TS; ++jj) t[i][jj] = fma(-pr[i], vc[jj], fma(-vr[i], pc[jj], t[i][jj]));
       }
@@ -474,14 +479,14 @@ __global__ void __launch_bounds__(256) tridiag_reg_kernel(int k, const double* _
     TRI_B(3)
   }
 #ifdef DAV_TRIDIAG_PROFILE
-  if (tid == 255) for (int q = 0; q < 4; ++q) scal[3 + q] = (double)cyc[q];
+  if (tid == (int)blockDim.x - 1) for (int q = 0; q < 4; ++q) scal[3 + q] = (double)cyc[q];
 #endif
 #undef TRI_TICK
 #undef TRI_A
 #undef TRI_B
   // the last 2 x 2 block and the trivial reflectors
 #pragma unroll
-  for (int i = 0; i < TS; ++i)
+  for (int i = 0; i < TSR; ++i)
 #pragma unroll
     for (int jj = 0; jj < TS; ++jj) {
       const int a = r0 + i, c = col(jj);
@@ -558,19 +563,45 @@ __global__ void __launch_bounds__(EW * 32) tri_eigvec_kernel(int k, const double
     double pm = 1.0, pc = ds[0] - x;
     bool neg = !(pc > 0.0);
     int cnt = neg;
-    for (int i = 1; i < k; ++i) {
+    // r02: blocks of 8 steps with the NEXT block's coefficients already in registers -- the recurrence is one
+    // dependent FMA per step, a shared-memory load inside the chain would triple its latency
+    int i = 1;
+    double dn[8], en[8];
+    if (i + 8 <= k) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { dn[q] = ds[i + q]; en[q] = e2s[i + q - 1]; }
+    }
+    for (; i + 8 <= k; i += 8) {
+      double dc[8], ec[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { dc[q] = dn[q]; ec[q] = en[q]; }
+      if (i + 16 <= k) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { dn[q] = ds[i + 8 + q]; en[q] = e2s[i + 8 + q - 1]; }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const double pn = fma(dc[q] - x, pc, -(ec[q] * pm));
+        const bool nneg = (pn == 0.0) ? !neg : (pn < 0.0);
+        cnt += nneg != neg;
+        neg = nneg;
+        pm = pc;
+        pc = pn;
+      }
+      {  // keep the pair inside the exponent range
+        const double mag = fmax(fabs(pc), fabs(pm));
+        const double f = mag > 1.0e100 ? 1.0e-100 : (mag < 1.0e-100 ? 1.0e100 : 1.0);
+        pc *= f;
+        pm *= f;
+      }
+    }
+    for (; i < k; ++i) {
       const double pn = fma(ds[i] - x, pc, -(e2s[i - 1] * pm));
       const bool nneg = (pn == 0.0) ? !neg : (pn < 0.0);
       cnt += nneg != neg;
       neg = nneg;
       pm = pc;
       pc = pn;
-      if ((i & 7) == 0) {  // keep the pair inside the exponent range
-        const double mag = fmax(fabs(pc), fabs(pm));
-        const double f = mag > 1.0e100 ? 1.0e-100 : (mag < 1.0e-100 ? 1.0e100 : 1.0);
-        pc *= f;
-        pm *= f;
-      }
     }
     const unsigned ok = __ballot_sync(0xffffffffu, cnt >= j + 1);
     const int first = ok ? (__ffs(ok) - 1) : 32;
@@ -813,6 +844,204 @@ __global__ void __launch_bounds__(1024) guard_kernel(int k, const double* __rest
   }
 }
 
+// ---- 3b. r02: the guard in two launches instead of five (small GEMM Y^T Y, ns_prepare, small GEMM Y G, small GEMM S Y,
+// guard_kernel: ~50 us of launch-bound work per Rayleigh-Ritz step).  One CTA takes GJ eigenvector columns j:
+//   g = Yraw^T yraw_j (one warp per column of Yraw)          defect_j = max |g - e_j|
+//   y_j = Yraw (1.5 e_j - 0.5 g)                             (the Newton-Schulz step, column j of it)
+//   s = S y_j,  theta_j = y_j.s / y_j.y_j,  resid_j = max |s - theta_j y_j|
+// and guard_accept_kernel takes the maxima and sets the accept flag.  Same arithmetic per entry as the GEMM form.
+constexpr int GJ = 4;
+__global__ void __launch_bounds__(256) guard_cols_kernel(int k, const double* __restrict__ Yraw,
+                                                         const double* __restrict__ Sfull, double* __restrict__ Y,
+                                                         double* __restrict__ w, double* __restrict__ defect,
+                                                         double* __restrict__ resid) {
+  extern __shared__ __align__(16) double sm[];
+  double* yr = sm;               // GJ x k: yraw_j
+  double* cf = yr + GJ * k;      // GJ x k: g, then the coefficients 1.5 e_j - 0.5 g
+  double* ys = cf + GJ * k;      // GJ x k: y_j
+  __shared__ double red[3][GJ][8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j0 = blockIdx.x * GJ;
+  const int nj = min(GJ, k - j0);
+  for (int e = tid; e < GJ * k; e += 256) {
+    const int q = e / k, r = e - q * k;
+    yr[e] = q < nj ? Yraw[(size_t)(j0 + q) * k + r] : 0.0;
+  }
+  __syncthreads();
+  // g(i, q) = Yraw(:, i) . yraw_q
+  for (int i = warp; i < k; i += 8) {
+    double a[GJ];
+#pragma unroll
+    for (int q = 0; q < GJ; ++q) a[q] = 0.0;
+    for (int r = lane; r < k; r += 32) {
+      const double v = Yraw[(size_t)i * k + r];
+#pragma unroll
+      for (int q = 0; q < GJ; ++q) a[q] = fma(v, yr[q * k + r], a[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < GJ; ++q) {
+      a[q] = warp_sum(a[q]);
+      if (lane == 0) cf[q * k + i] = a[q];
+    }
+  }
+  __syncthreads();
+  // defect and Newton-Schulz coefficients
+  double dmax[GJ];
+#pragma unroll
+  for (int q = 0; q < GJ; ++q) dmax[q] = 0.0;
+  for (int e = tid; e < GJ * k; e += 256) {
+    const int q = e / k, i = e - q * k;
+    const double gv = cf[e], id = (i == j0 + q) ? 1.0 : 0.0;
+    const double dev = fabs(gv - id);
+    const double dv = (dev == dev) ? dev : 1.0e300;
+#pragma unroll
+    for (int qq = 0; qq < GJ; ++qq)
+      if (qq == q && q < nj) dmax[qq] = fmax(dmax[qq], dv);
+    cf[e] = 1.5 * id - 0.5 * gv;
+  }
+#pragma unroll
+  for (int q = 0; q < GJ; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dmax[q] = fmax(dmax[q], __shfl_xor_sync(0xffffffffu, dmax[q], o));
+    if (lane == 0) red[0][q][warp] = dmax[q];
+  }
+  __syncthreads();
+  if (tid < nj) {
+    double m = 0.0;
+    for (int x = 0; x < 8; ++x) m = fmax(m, red[0][tid][x]);
+    defect[j0 + tid] = m;
+  }
+  // y_q(r) = sum_i Yraw(r, i) c(i, q): row r by `parts` threads, each a strided share of the columns (k <= 128
+  // would leave half of the CTA idle and every thread with a chain of k dependent-latency loads)
+  const int parts = k >= 256 ? 1 : 256 / k;
+  double* pp = ys + GJ * k;  // parts x GJ x k partial sums (parts > 1)
+  for (int e = tid; e < parts * k || (parts == 1 && e < k); e += 256) {
+    const int part = e / k, r = e - part * k;
+    double a[GJ];
+#pragma unroll
+    for (int q = 0; q < GJ; ++q) a[q] = 0.0;
+#pragma unroll 8
+    for (int i = part; i < k; i += parts) {
+      const double v = Yraw[(size_t)i * k + r];
+#pragma unroll
+      for (int q = 0; q < GJ; ++q) a[q] = fma(v, cf[q * k + i], a[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < GJ; ++q) pp[(part * GJ + q) * k + r] = a[q];
+  }
+  __syncthreads();
+  for (int e = tid; e < GJ * k; e += 256) {
+    const int q = e / k, r = e - q * k;
+    double a = 0.0;
+    for (int part = 0; part < parts; ++part) a += pp[(part * GJ + q) * k + r];
+    ys[e] = a;
+    if (q < nj) Y[(size_t)(j0 + q) * k + r] = a;
+  }
+  __syncthreads();
+  // s = S y (same split), Rayleigh quotient and residual
+  for (int e = tid; e < parts * k || (parts == 1 && e < k); e += 256) {
+    const int part = e / k, r = e - part * k;
+    double a[GJ];
+#pragma unroll
+    for (int q = 0; q < GJ; ++q) a[q] = 0.0;
+#pragma unroll 8
+    for (int c = part; c < k; c += parts) {
+      const double v = Sfull[(size_t)c * k + r];  // S symmetric: column c read along r
+#pragma unroll
+      for (int q = 0; q < GJ; ++q) a[q] = fma(v, ys[q * k + c], a[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < GJ; ++q) pp[(part * GJ + q) * k + r] = a[q];
+  }
+  __syncthreads();
+  double yy[GJ], sy[GJ];
+#pragma unroll
+  for (int q = 0; q < GJ; ++q) yy[q] = sy[q] = 0.0;
+  for (int e = tid; e < GJ * k; e += 256) {
+    const int q = e / k, r = e - q * k;
+    double a = 0.0;
+    for (int part = 0; part < parts; ++part) a += pp[(part * GJ + q) * k + r];
+    yr[e] = a;  // yraw is no longer needed: keep s there
+    const double yv = ys[e];
+#pragma unroll
+    for (int qq = 0; qq < GJ; ++qq)
+      if (qq == q) {
+        yy[qq] = fma(yv, yv, yy[qq]);
+        sy[qq] = fma(yv, a, sy[qq]);
+      }
+  }
+#pragma unroll
+  for (int q = 0; q < GJ; ++q) {
+    yy[q] = warp_sum(yy[q]);
+    sy[q] = warp_sum(sy[q]);
+    if (lane == 0) { red[1][q][warp] = yy[q]; red[2][q][warp] = sy[q]; }
+  }
+  __syncthreads();
+  double th[GJ];
+#pragma unroll
+  for (int q = 0; q < GJ; ++q) {
+    double a = 0.0, b = 0.0;
+    for (int x = 0; x < 8; ++x) { a += red[1][q][x]; b += red[2][q][x]; }
+    th[q] = b / a;
+  }
+  double rmax[GJ];
+#pragma unroll
+  for (int q = 0; q < GJ; ++q) rmax[q] = 0.0;
+  for (int r = tid; r < k; r += 256) {
+#pragma unroll
+    for (int q = 0; q < GJ; ++q) {
+      const double x = fabs(yr[q * k + r] - th[q] * ys[q * k + r]);
+      rmax[q] = (x == x) ? fmax(rmax[q], x) : 1.0e300;
+    }
+  }
+  __syncthreads();  // red[0] is reused
+#pragma unroll
+  for (int q = 0; q < GJ; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rmax[q] = fmax(rmax[q], __shfl_xor_sync(0xffffffffu, rmax[q], o));
+    if (lane == 0) red[0][q][warp] = rmax[q];
+  }
+  __syncthreads();
+  if (tid < nj) {
+    double m = 0.0;
+    for (int x = 0; x < 8; ++x) m = fmax(m, red[0][tid][x]);
+    // (a NaN quotient makes every |s - theta y| NaN, which the loop above turned into 1e300)
+    resid[j0 + tid] = m;
+    double tq = 0.0;
+#pragma unroll
+    for (int q = 0; q < GJ; ++q) if (q == tid) tq = th[q];
+    w[j0 + tid] = tq;
+  }
+}
+
+__global__ void __launch_bounds__(256) guard_accept_kernel(int k, const double* __restrict__ defect,
+                                                           const double* __restrict__ resid,
+                                                           const double* __restrict__ scal, double* flagv,
+                                                           int* accept) {
+  __shared__ double red[2][8];
+  double d = 0.0, r = 0.0;
+  for (int j = threadIdx.x; j < k; j += 256) {
+    d = fmax(d, defect[j]);
+    r = fmax(r, resid[j]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    d = fmax(d, __shfl_xor_sync(0xffffffffu, d, o));
+    r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = d; red[1][threadIdx.x >> 5] = r; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double dm = 0.0, rm = 0.0;
+    for (int i = 0; i < 8; ++i) { dm = fmax(dm, red[0][i]); rm = fmax(rm, red[1][i]); }
+    flagv[1] = dm;
+    flagv[2] = rm;
+    const double smax = scal[0];
+    const bool ok = (dm <= 3.0e-8) && (rm <= 64.0 * k * EPS * smax) && (smax <= 1.0e150);
+    *accept = ok ? 1 : 0;
+  }
+}
+
 int env_int(const char* name, int dflt) {
   const char* e = std::getenv(name);
   return e ? std::atoi(e) : dflt;
@@ -868,9 +1097,14 @@ void sym_eigh(cudaStream_t s, int k, double* S, double* Y, double* w, double* sc
   static const int reg_env = env_int("DAV_TRIDIAG_REG", 1);
   if (reg_env != 0 && k <= 128) {
     // register-resident matrix (r02): 16 x 16 threads, TS x TS tile each
-    if (k <= 32) tridiag_reg_kernel<2><<<1, 256, 0, s>>>(k, S, Sfull, Vh, tau, d, e, flagv);
-    else if (k <= 64) tridiag_reg_kernel<4><<<1, 256, 0, s>>>(k, S, Sfull, Vh, tau, d, e, flagv);
-    else tridiag_reg_kernel<8><<<1, 256, 0, s>>>(k, S, Sfull, Vh, tau, d, e, flagv);
+    // (16 warps for k > 32: one warp issues a DFMA only every ~4 cycles, so the FP64 pipe of the SM needs >= 4
+    // warps per scheduler; DAV_TRIDIAG_WARPS=8 selects the 8-warp tiling)
+    static const int w8 = env_int("DAV_TRIDIAG_WARPS", 16) == 8;
+    if (k <= 32) tridiag_reg_kernel<2, 2><<<1, 256, 0, s>>>(k, S, Sfull, Vh, tau, d, e, flagv);
+    else if (k <= 64 && w8) tridiag_reg_kernel<4, 4><<<1, 256, 0, s>>>(k, S, Sfull, Vh, tau, d, e, flagv);
+    else if (k <= 64) tridiag_reg_kernel<2, 4><<<1, 512, 0, s>>>(k, S, Sfull, Vh, tau, d, e, flagv);
+    else if (w8) tridiag_reg_kernel<8, 8><<<1, 256, 0, s>>>(k, S, Sfull, Vh, tau, d, e, flagv);
+    else tridiag_reg_kernel<4, 8><<<1, 512, 0, s>>>(k, S, Sfull, Vh, tau, d, e, flagv);
   } else {
     // the step loop is instruction-issue bound on per-warp bookkeeping, not on the m^2 FMAs: few warps for small k
     static const int thr_env = env_int("DAV_TRIDIAG_THREADS", 0);
@@ -900,15 +1134,28 @@ void sym_eigh(cudaStream_t s, int k, double* S, double* Y, double* w, double* sc
     CK_LAUNCH();
     ++g_kernel_launches;
   }
-  small_gemm(s, true, k, Yraw, Yraw, G);
-  ns_prepare_kernel<<<1, 1024, 0, s>>>(k, G, flagv);
-  CK_LAUNCH();
-  ++g_kernel_launches;
-  small_gemm(s, false, k, Yraw, G, Y);
-  small_gemm(s, false, k, Sfull, Y, SY);
-  guard_kernel<<<1, 1024, 0, s>>>(k, Y, SY, flagv, w, flagv, accept);
-  CK_LAUNCH();
-  ++g_kernel_launches;
+  static const int fused_guard = env_int("DAV_GUARD_FUSED", 1);
+  if (fused_guard != 0) {
+    // G (k^2 doubles) is free in this form: its head holds the per-column defects and residuals
+    const size_t gsm = (3 + (size_t)(k >= 256 ? 1 : 256 / k)) * GJ * k * sizeof(double);
+    if (gsm > 40 * 1024) ensure_dyn_smem(guard_cols_kernel, 64 * 1024);
+    guard_cols_kernel<<<(k + GJ - 1) / GJ, 256, gsm, s>>>(k, Yraw, Sfull, Y, w, G, G + k);
+    CK_LAUNCH();
+    ++g_kernel_launches;
+    guard_accept_kernel<<<1, 256, 0, s>>>(k, G, G + k, flagv, flagv, accept);
+    CK_LAUNCH();
+    ++g_kernel_launches;
+  } else {
+    small_gemm(s, true, k, Yraw, Yraw, G);
+    ns_prepare_kernel<<<1, 1024, 0, s>>>(k, G, flagv);
+    CK_LAUNCH();
+    ++g_kernel_launches;
+    small_gemm(s, false, k, Yraw, G, Y);
+    small_gemm(s, false, k, Sfull, Y, SY);
+    guard_kernel<<<1, 1024, 0, s>>>(k, Y, SY, flagv, w, flagv, accept);
+    CK_LAUNCH();
+    ++g_kernel_launches;
+  }
   // Jacobi runs only when the guard rejected the fast path (device-side decision)
   jacobi_eigh(s, k, S, Y, w, scratch, status, accept);
 }
