@@ -163,21 +163,30 @@ __device__ __forceinline__ void reduce_store(const ReduceOut& o, int64_t M, int6
 // gather_seg >= 0: no rank sum; out.C[...] receives every rank's words (two-segment all-gather, see allgather2).
 __global__ void __launch_bounds__(256) ll_reduce_kernel(LLArgs a, const double* __restrict__ src, int splits,
                                                         int64_t M, int64_t total, size_t cap, unsigned flag, int par,
-                                                        ReduceOut out, int64_t gather_seg, int* error) {
+                                                        ReduceOut out, int64_t gather_seg, int* error, int sg) {
   const int P = a.world, r = a.rank;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int z = 0;
-    for (; z + 3 < splits; z += 4) {
-      s0 += src[(size_t)z * total + e];
-      s1 += src[(size_t)(z + 1) * total + e];
-      s2 += src[(size_t)(z + 2) * total + e];
-      s3 += src[(size_t)(z + 3) * total + e];
+  // r02: `sg` (1, 2, 4 or 8) neighbouring lanes share one output word: each sums every sg-th split-K partial (two
+  // chains), the group adds up by a fixed butterfly (same bits on every lane and rank), lane 0 of the group goes on.
+  // With ~130 partials per word one thread per word was a chain of ~33 dependent L2 round trips (17 us).
+  const int sub = threadIdx.x & (sg - 1);
+  const int64_t gid0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / sg;
+  const int64_t gstride = (int64_t)gridDim.x * blockDim.x / sg;
+  const int64_t rounds = (total + gstride - 1) / gstride;  // every lane of a warp runs the same number of rounds
+  for (int64_t it = 0; it < rounds; ++it) {
+    const int64_t e = gid0 + it * gstride;
+    const bool live = e < total;
+    double s0 = 0.0, s1 = 0.0;
+    if (live) {
+      int z = sub;
+      for (; z + sg < splits; z += 2 * sg) {
+        s0 += src[(size_t)z * total + e];
+        s1 += src[(size_t)(z + sg) * total + e];
+      }
+      if (z < splits) s0 += src[(size_t)z * total + e];
     }
-    if (z < splits) s0 += src[(size_t)z * total + e];
-    if (z + 1 < splits) s1 += src[(size_t)(z + 1) * total + e];
-    if (z + 2 < splits) s2 += src[(size_t)(z + 2) * total + e];
-    double v = ((s0 + s1) + s2) + s3;
+    double v = s0 + s1;
+    for (int o = sg >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (!live || sub != 0) continue;
     if (P > 1) {
       const size_t line = ((size_t)par * P + r) * cap + (size_t)e;
 #pragma unroll 4
@@ -563,9 +572,10 @@ void Comm::launch_ll(const double* src, int splits, int64_t M, int64_t total, co
     par = (int)(ar_epoch_ & 1ULL);
     ++peer_calls;
   }
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, 256), 1184));
+  const int sg = splits >= 32 ? 8 : (splits >= 8 ? 4 : (splits >= 2 ? 2 : 1));
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total * sg, 256), 1184));
   ll_reduce_kernel<<<grid, 256, 0, s>>>(a, src, splits, M, total, slot_cap_, flag, par, out, gather_seg,
-                                        a.world > 1 ? &((PeerCtl*)ctl_.local)->error : nullptr);
+                                        a.world > 1 ? &((PeerCtl*)ctl_.local)->error : nullptr, sg);
   CK_LAUNCH();
   ++g_kernel_launches;
 }

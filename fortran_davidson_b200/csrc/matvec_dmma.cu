@@ -435,19 +435,33 @@ __global__ void __launch_bounds__(THREADS, 1)
   }
 }
 
-// Adds the partial tiles of every row tile that was split over several CTAs, in CTA order.
-__global__ void fixup_kernel(int BM, int BPAD, Params p) {
+// Adds the partial tiles of every row tile that was split over several CTAs, in CTA order.  grid = (remainder tiles,
+// FIXUP_SPLIT): the pieces of a tile are looked up once per CTA (the lookup divides), every thread then adds its
+// elements piece by piece (r02: was one CTA per tile with the lookup inside the element loop, 35-52 us per launch at
+// 12,500 local rows).
+constexpr int FIXUP_SPLIT = 4;
+constexpr int FIXUP_MAX_PIECES = 64;
+__global__ void __launch_bounds__(256) fixup_kernel(int BM, int BPAD, Params p) {
+  __shared__ int piece_off[FIXUP_MAX_PIECES];
   const int rt = blockIdx.x;  // tile of the remainder
   const int tile = p.sc.tile_off + rt;
   const int count = fixup_count(p.sc, rt);
   if (count == 0) return;  // written directly
   const int elems = BM * BPAD;
-  for (int e = threadIdx.x; e < elems; e += blockDim.x) {
+  const int cached = min(count, FIXUP_MAX_PIECES);
+  for (int i = threadIdx.x; i < cached; i += blockDim.x) {
+    int cta, slot;
+    fixup_piece(p.sc, rt, i, cta, slot);
+    piece_off[i] = cta * WS_SLOTS + slot;
+  }
+  __syncthreads();
+  for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < elems; e += gridDim.y * blockDim.x) {
     const int r = e % BM, j = e / BM;
     const int64_t row = (int64_t)tile * BM + r;
     if (row >= p.M || j >= p.b) continue;
     double s = 0.0;
-    for (int i = 0; i < count; ++i) {
+    for (int i = 0; i < cached; ++i) s += p.ws[(size_t)piece_off[i] * (size_t)elems + e];
+    for (int i = cached; i < count; ++i) {
       int cta, slot;
       fixup_piece(p.sc, rt, i, cta, slot);
       s += p.ws[((size_t)cta * WS_SLOTS + slot) * (size_t)elems + e];
@@ -496,7 +510,7 @@ void launch_cfg(cudaStream_t s, const CUtensorMap& map, Params& p, int ksteps, i
   CK_LAUNCH();
   ++g_kernel_launches;
   if (rem_tiles > 0) {
-    fixup_kernel<<<rem_tiles, 256, 0, s>>>(BM, BPAD, p);
+    fixup_kernel<<<dim3(rem_tiles, FIXUP_SPLIT), 256, 0, s>>>(BM, BPAD, p);
     CK_LAUNCH();
     ++g_kernel_launches;
   }

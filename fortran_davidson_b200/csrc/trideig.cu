@@ -313,8 +313,9 @@ __global__ void __launch_bounds__(256 * TS / TSR) tridiag_reg_kernel(int k, cons
       double x = 0.0;
       if (a < k && c < k) {
         x = S_in[min(a, c) + (size_t)max(a, c) * k];  // DSYEV 'U': only the upper triangle is read
-        Sfull[a + (size_t)c * k] = x;
-        Vh[a + (size_t)c * k] = 0.0;
+        // the symmetrised copy for the guard, written at the MIRRORED position: the 16 lanes of a tile row then
+        // store 256 contiguous bytes (entry (c, a) = entry (a, c))
+        Sfull[c + (size_t)a * k] = x;
       }
       t[i][jj] = x;
       mx = fmax(mx, fabs(x));  // NaN is dropped here and caught by the guard
@@ -323,6 +324,9 @@ __global__ void __launch_bounds__(256 * TS / TSR) tridiag_reg_kernel(int k, cons
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((tid & 31) == 0) red[warp] = mx;
   for (int i = tid; i < KP; i += blockDim.x) pb[i] = 0.0;
+  // reflector columns k-2, k-1 do not exist (the loop writes every other column of Vh completely)
+  for (int i = tid; i < 2 * k; i += blockDim.x)
+    if (k >= 2) Vh[(size_t)(k - 2) * k + i] = 0.0;
 
   // The warp that owns row jn builds reflector jn from it: v -> vb (and Vh), tau -> tjb (and tau[]), d, e.  The
   // step loop keeps its code small on purpose (one SM's instruction cache serves 8 warps in lock step): the row is
