@@ -107,6 +107,13 @@ module davidson_b200_c
        integer(c_int) :: ierr
      end function dav_norm
 
+     pure function dav_norm_value(n, vector) bind(C, name="dav_norm_value") result(res)
+       import :: c_int64_t, c_double
+       integer(c_int64_t), value :: n
+       real(c_double), intent(in) :: vector(*)
+       real(c_double) :: res
+     end function dav_norm_value
+
      function dav_lapack_generalized_eigensolver(dim, mtx, stx, eigenvalues, eigenvectors) &
           bind(C, name="dav_lapack_generalized_eigensolver") result(ierr)
        import :: c_ptr, c_int, c_double
@@ -297,7 +304,13 @@ contains
     real(dp) :: scalar
     scalar = 1.d0
     if (present(alpha)) scalar = alpha
-    allocate(rs(size(mtx, 1)))
+    ! op(mtx) * vector has size(mtx, 2) entries for transA = 'T' (the reference allocates size(mtx, 1) in both
+    ! cases, lapack_wrapper.f90:349, which only works for square matrices)
+    if (transA == 'T' .or. transA == 't') then
+       allocate(rs(size(mtx, 2)))
+    else
+       allocate(rs(size(mtx, 1)))
+    end if
     rs = 0.d0
     a = mtx
     v = vector
@@ -348,13 +361,12 @@ contains
     end do
   end function eye
 
-  function norm(vector)
-    !> array_utils.f90:46-53
+  pure function norm(vector)
+    !> array_utils.f90:46-53 -- `pure` like the reference, so that callers may use it in pure / elemental contexts.
+    !> dav_norm_value has no side effect a Fortran program can observe and returns NaN instead of an error code.
     real(dp), dimension(:), intent(in) :: vector
     real(dp) :: norm
-    real(dp), dimension(:), allocatable :: v
-    v = vector
-    call check_status(dav_norm(int(size(v), c_int64_t), v, norm), "norm")
+    norm = dav_norm_value(int(size(vector), c_int64_t), vector)
   end function norm
 
   subroutine concatenate(arr, brr)
@@ -514,7 +526,9 @@ contains
     integer, intent(in), optional :: max_dim_sub
     real(dp), intent(in) :: tolerance
     character(len=*), intent(in) :: method
-    integer, intent(out) :: iters
+    !> the reference declares intent(out) but leaves `iters` unassigned when the loop does not converge
+    !> (davidson.f90:417); its value on entry is therefore handed through, which needs intent(inout)
+    integer, intent(inout) :: iters
     procedure(gemv_like) :: fun_matrix_gemv, fun_second_matrix_gemv
 
     real(dp), dimension(:, :), allocatable :: vec

@@ -11,17 +11,20 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DAV_B200_LIB") or os.path.join(HERE, "libdavidson_b200.so")
 
 GEMV_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int64, C.c_int64, C.c_void_p)
+# device functor: (d_x, ldx, d_y, ldy, n, b, row_begin, nrows, cuda_stream, ctx), raw device addresses
+DEVICE_GEMV_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                             C.c_int64, C.c_void_p, C.c_void_p)
 
 # every symbol include/davidson_b200.h declares
 SYMBOLS = [
-    "dav_last_error", "dav_version", "dav_device_count", "dav_generalized_eigensolver_dense",
+    "dav_last_error", "dav_version", "dav_device_count", "dav_set_default_device", "dav_generalized_eigensolver_dense",
     "dav_generalized_eigensolver_free", "dav_generalized_eigensolver_free_builtin", "dav_get_unique_id",
     "dav_create", "dav_create_distributed", "dav_destroy", "dav_alloc_pinned", "dav_free_pinned", "dav_partition_rows",
     "dav_matrix_generate_diagonal_dominant", "dav_matrix_upload", "dav_matrix_upload_rows",
     "dav_matrix_set_operator",
-    "dav_matrix_set_callback", "dav_matrix_clear", "dav_matrix_download", "dav_solve", "dav_solve_local", "dav_get_stats",
+    "dav_matrix_set_callback", "dav_matrix_set_device_callback", "dav_matrix_clear", "dav_matrix_download", "dav_solve", "dav_solve_local", "dav_get_stats",
     "dav_set_matvec_impl", "dav_block_matvec", "dav_bench_block_matvec", "dav_generate_diagonal_dominant",
-    "dav_generate_preconditioner", "dav_norm", "dav_lapack_generalized_eigensolver",
+    "dav_generate_preconditioner", "dav_norm", "dav_norm_value", "dav_lapack_generalized_eigensolver",
     "dav_lapack_generalized_eigensolver_lowest", "dav_sym_eigh_info", "dav_lapack_qr", "dav_lapack_solver", "dav_lapack_matmul",
     "dav_lapack_matrix_vector", "dav_lapack_sort", "dav_free_matmul", "dav_compute_on_the_fly",
     "dav_debug_matvec_schedule", "dav_bench_fp64_pipe", "dav_debug_matvec_rect", "dav_debug_collective",

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libdavidson_b200.so")
 SOURCES = ["capi.cu", "solver.cu", "comm.cu", "dgemm.cu", "smalldense.cu", "trideig.cu", "vecops.cu", "freeops.cu", "freeops_dmma.cu",
-           "matvec_dmma.cu", "gjd.cu", "microbench.cu"]
+           "matvec_dmma.cu", "gjd.cu", "microbench.cu", "densesolve.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = (["-DDAV_TRIDIAG_PROFILE=" + os.environ["DAV_TRIDIAG_PROFILE"]] if os.environ.get("DAV_TRIDIAG_PROFILE") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr", "--extended-lambda"]

@@ -46,6 +46,15 @@ void need(bool cond, const char* what) {
 }
 
 // small RAII context for the utility entry points: device 0 (or the current one), own stream
+// Device of the calls that take no handle (the drop-in solver calls and the lapack_wrapper / array_utils mirrors):
+// dav_set_default_device(), else the environment variable DAV_DEVICE, else device 0.
+int g_default_device = -1;
+int default_device() {
+  if (g_default_device >= 0) return g_default_device;
+  const char* e = std::getenv("DAV_DEVICE");
+  return e ? std::max(0, std::atoi(e)) : 0;
+}
+
 struct Ctx {
   cudaStream_t s = nullptr;
   Ctx() {
@@ -55,6 +64,9 @@ struct Ctx {
       (void)cudaGetLastError();
       DAV_THROW(DAV_ERR_CUDA, "no CUDA device available; this library has no CPU fallback");
     }
+    const int dev = default_device();
+    if (dev >= count) DAV_THROW(DAV_ERR_INVALID, "default device %d out of range (%d devices)", dev, count);
+    CK(cudaSetDevice(dev));
     CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   }
   ~Ctx() {
@@ -119,6 +131,18 @@ int dav_device_count(void) {
     return 0;
   }
   return count;
+}
+
+int dav_set_default_device(int device) {
+  API_BEGIN
+  need(device >= -1, "device must be >= 0 (or -1: back to DAV_DEVICE / 0)");
+  if (device >= 0) {
+    const int count = dav_device_count();
+    need(count > 0, "no CUDA device available; this library has no CPU fallback");
+    need(device < count, "device out of range");
+  }
+  g_default_device = device;
+  API_END
 }
 
 int dav_alloc_pinned(size_t bytes, void** ptr) {
@@ -263,6 +287,14 @@ int dav_matrix_set_callback(dav_solver_t* h, int which, int64_t n, dav_gemv_fn f
   API_BEGIN
   need(h && (which == 0 || which == 1), "bad handle / slot");
   h->set_callback(which, n, fn, ctx, diag);
+  API_END
+}
+
+int dav_matrix_set_device_callback(dav_solver_t* h, int which, int64_t n, dav_device_gemv_fn fn, void* ctx,
+                                   const double* diag) {
+  API_BEGIN
+  need(h && (which == 0 || which == 1), "bad handle / slot");
+  h->set_device_callback(which, n, fn, ctx, diag);
   API_END
 }
 
@@ -490,7 +522,7 @@ int dav_generalized_eigensolver_dense(int64_t n, const double* matrix, int64_t l
   API_BEGIN
   need(matrix && eigenvalues && eigenvectors && iters, "NULL argument");
   const int m = parse_method(method);
-  std::unique_ptr<dav_solver> s(new dav_solver(0, 0, 1, nullptr));
+  std::unique_ptr<dav_solver> s(new dav_solver(default_device(), 0, 1, nullptr));
   s->upload(0, n, matrix, lda);
   if (second_matrix) s->upload(1, n, second_matrix, ldb);
   s->solve(lowest, m, max_iterations, tolerance, max_dim_sub, eigenvalues, eigenvectors, ldv, iters);
@@ -505,7 +537,7 @@ int dav_generalized_eigensolver_free(int64_t n, dav_gemv_fn fun_matrix_gemv, voi
   API_BEGIN
   need(fun_matrix_gemv && fun_second_matrix_gemv && eigenvalues && ritz_vectors && iters, "NULL argument");
   const int m = parse_method(method);
-  std::unique_ptr<dav_solver> s(new dav_solver(0, 0, 1, nullptr));
+  std::unique_ptr<dav_solver> s(new dav_solver(default_device(), 0, 1, nullptr));
   s->set_callback(0, n, fun_matrix_gemv, ctx_matrix, diag_matrix);
   s->set_callback(1, n, fun_second_matrix_gemv, ctx_second, diag_second_matrix);
   s->solve(lowest, m, max_iterations, tolerance, max_dim_sub, eigenvalues, ritz_vectors, ldv, iters);
@@ -519,7 +551,7 @@ int dav_generalized_eigensolver_free_builtin(int64_t n, int op_matrix, int op_se
   API_BEGIN
   need(eigenvalues && ritz_vectors && iters, "NULL argument");
   const int m = parse_method(method);
-  std::unique_ptr<dav_solver> s(new dav_solver(0, 0, 1, nullptr));
+  std::unique_ptr<dav_solver> s(new dav_solver(default_device(), 0, 1, nullptr));
   s->set_operator(0, n, op_matrix);
   s->set_operator(1, n, op_second_matrix);
   s->solve(lowest, m, max_iterations, tolerance, max_dim_sub, eigenvalues, ritz_vectors, ldv, iters);
@@ -564,6 +596,12 @@ int dav_generate_preconditioner(int64_t n, const double* diag, int dim_sub, doub
     precond[(size_t)j * ld + hidx[j]] = 1.0;
   }
   API_END
+}
+
+double dav_norm_value(int64_t n, const double* vector) {
+  double r = 0.0;
+  if (dav_norm(n, vector, &r) != DAV_OK) return std::nan("");
+  return r;
 }
 
 int dav_norm(int64_t n, const double* vector, double* result) {
@@ -662,32 +700,52 @@ int dav_lapack_qr(int64_t m, int n, double* basis, int64_t ld) {
     gemm(c.s, false, m, n, n, 1.0, cur, m, Rinv.p, n, 0.0, other, m, nullptr, 0);
     std::swap(cur, other);
   }
-  check_status_dev(c, status.p, "lapack_qr (rank deficient basis)");
+  int hst = 0;
+  CK(cudaMemcpyAsync(&hst, status.p, sizeof(int), cudaMemcpyDeviceToHost, c.s));
+  c.sync();
+  if (hst != 0) {
+    // rank-deficient / ill-conditioned basis: DGEQRF + DORGQR (lapack_wrapper.f90:176-236) never fail, they return an
+    // orthonormal basis that contains the span of the input.  Same contract through the solver's SVQB loop
+    // (Jacobi on the scaled Gram matrix, deficient directions refilled, repeated until orthonormal).
+    std::unique_ptr<dav_solver> sv(new dav_solver(default_device(), 0, 1, nullptr));
+    sv->set_dims(m);
+    sv->alloc_work(1, std::max(n, 2));
+    CK(cudaMemcpy2DAsync(sv->C.p, (size_t)sv->ldv * 8, basis, (size_t)ld * 8, (size_t)m * 8, (size_t)n,
+                         cudaMemcpyHostToDevice, sv->stream));
+    sv->orthonormalize_block(sv->C.p, n, 0, sv->C.p);
+    CK(cudaMemcpy2DAsync(basis, (size_t)ld * 8, sv->C.p, (size_t)sv->ldv * 8, (size_t)m * 8, (size_t)n,
+                         cudaMemcpyDeviceToHost, sv->stream));
+    CK(cudaStreamSynchronize(sv->stream));
+    return DAV_OK;
+  }
   CK(cudaMemcpy2DAsync(basis, (size_t)ld * 8, cur, (size_t)m * 8, (size_t)m * 8, (size_t)n, cudaMemcpyDeviceToHost,
                        c.s));
   c.sync();
   API_END
 }
 
-// Symmetric solve through the Jacobi eigendecomposition arr = V W V^T: x = V (V^T b / w).
+// DSYSV('U') (lapack_wrapper.f90:238-277): arr x = brr for a symmetric matrix of which only the upper triangle is
+// read; brr <- x.  Entirely on the device: symmetrise, blocked LU with partial pivoting (csrc/densesolve.cu), back
+// substitution.  (r01 went through an eigendecomposition and host loops, n <= 1024.)
 int dav_lapack_solver(int n, const double* arr, double* brr) {
   API_BEGIN
   need(n >= 1 && arr && brr, "bad arguments");
-  need(n <= 1024, "dav_lapack_solver: n <= 1024 supported (the solver's GJD path uses block MINRES instead)");
   Ctx c;
-  std::vector<double> w(n), v((size_t)n * n), y(n);
-  eigensolve_dev(c, n, arr, nullptr, w.data(), v.data(), n);
-  for (int j = 0; j < n; ++j) {
-    double s = 0.0;
-    for (int i = 0; i < n; ++i) s += v[(size_t)j * n + i] * brr[i];
-    if (w[j] == 0.0) DAV_THROW(DAV_ERR_NOT_POSDEF, "lapack_solver: singular matrix");
-    y[j] = s / w[j];
-  }
-  for (int i = 0; i < n; ++i) {
-    double s = 0.0;
-    for (int j = 0; j < n; ++j) s += v[(size_t)j * n + i] * y[j];
-    brr[i] = s;
-  }
+  DevBuf<double> A;
+  DevBuf<int> piv, status;
+  A.alloc((size_t)n * (n + 1));
+  piv.alloc(n);
+  status.alloc(1);
+  CK(cudaMemsetAsync(status.p, 0, sizeof(int), c.s));
+  h2d(A.p, arr, (size_t)n * n, c.s);
+  h2d(A.p + (size_t)n * n, brr, n, c.s);
+  symmetrize_from_upper(c.s, n, A.p, n);
+  lu_solve(c.s, n, 1, A.p, n, piv.p, status.p);
+  int hst = 0;
+  CK(cudaMemcpyAsync(&hst, status.p, sizeof(int), cudaMemcpyDeviceToHost, c.s));
+  d2h(brr, A.p + (size_t)n * n, n, c.s);
+  c.sync();
+  if (hst != 0) DAV_THROW(DAV_ERR_NOT_POSDEF, "lapack_solver: singular matrix (or NaN input)");
   API_END
 }
 
@@ -704,12 +762,12 @@ int dav_lapack_matmul(char transA, char transB, int64_t rows_a, int64_t cols_a, 
   A.alloc((size_t)rows_a * cols_a); B.alloc((size_t)k * n); Cm.alloc((size_t)m * n);
   ws.alloc(std::max<size_t>((size_t)m * n * 16, (size_t)1 << 20));
   h2d(A.p, arr, (size_t)rows_a * cols_a, c.s);
-  std::vector<double> bt;
-  if (transB == 'T') {  // op(B) = B^T: transpose on the host, the device GEMM takes B as stored K x N
-    bt.resize((size_t)k * n);
-    for (int64_t i = 0; i < rows_b; ++i)
-      for (int64_t j = 0; j < cols_b; ++j) bt[(size_t)i * k + j] = brr[(size_t)j * rows_b + i];
-    h2d(B.p, bt.data(), (size_t)k * n, c.s);
+  if (transB == 'T') {  // op(B) = B^T: the device GEMM takes B as stored K x N
+    DevBuf<double> Bt;
+    Bt.alloc((size_t)rows_b * cols_b);
+    h2d(Bt.p, brr, (size_t)rows_b * cols_b, c.s);
+    transpose(c.s, rows_b, cols_b, Bt.p, rows_b, B.p, k);
+    c.sync();  // Bt goes out of scope
   } else {
     h2d(B.p, brr, (size_t)k * n, c.s);
   }
@@ -741,40 +799,25 @@ int dav_lapack_sort(char id, int64_t n, double* vector, int32_t* keys) {
   API_BEGIN
   need(vector && keys && n >= 1 && (id == 'I' || id == 'D'), "bad arguments");
   Ctx c;
-  std::vector<double> h(vector, vector + n);
-  if (id == 'D')
-    for (auto& v : h) v = -v;
-  // ranks by selection of the (up to 1024) smallest, repeated on the remainder: the device path used by the
-  // solver (top-2L of the diagonal) generalised to a full ordering
-  DevBuf<double> d, val, sv;
-  DevBuf<int64_t> idx, gi, si;
+  // DLASRT + the permutation (lapack_wrapper.f90:367-392): one bitonic sort of (value, position) pairs on the device;
+  // keys[original position] = 1-based rank, ties in the original order
+  const int64_t np = sort_pairs_padded(n);
+  DevBuf<double> d, key;
+  DevBuf<int64_t> idx;
   DevBuf<int> status;
-  d.alloc(n); gi.alloc(n); status.alloc(1);
-  const int kmax = (int)std::min<int64_t>(n, 1024);
-  val.alloc(kmax); idx.alloc(kmax);
-  sv.alloc(topk_scratch_entries(n, kmax)); si.alloc(topk_scratch_entries(n, kmax));
+  d.alloc(n); key.alloc(np); idx.alloc(np); status.alloc(1);
   CK(cudaMemsetAsync(status.p, 0, sizeof(int), c.s));
-  std::vector<int64_t> hg(n), hidx(kmax);
-  std::vector<double> hv(kmax);
-  for (int64_t t = 0; t < n; ++t) hg[t] = t;
-  std::vector<double> sorted(n);
-  int64_t done = 0;
-  while (done < n) {
-    const int kk = (int)std::min<int64_t>(kmax, n - done);
-    h2d(d.p, h.data(), n, c.s);
-    CK(cudaMemcpyAsync(gi.p, hg.data(), (size_t)n * 8, cudaMemcpyHostToDevice, c.s));
-    topk_smallest(c.s, d.p, gi.p, n, 0, kk, val.p, idx.p, status.p, sv.p, si.p);
-    CK(cudaMemcpyAsync(hidx.data(), idx.p, (size_t)kk * 8, cudaMemcpyDeviceToHost, c.s));
-    d2h(hv.data(), val.p, kk, c.s);
-    check_status_dev(c, status.p, "lapack_sort");
-    for (int t = 0; t < kk; ++t) {
-      sorted[done + t] = hv[t];
-      keys[hidx[t]] = (int32_t)(done + t + 1);
-      hg[hidx[t]] = -1;  // consumed: padding for the next round
-    }
-    done += kk;
+  h2d(d.p, vector, n, c.s);
+  sort_pairs(c.s, n, d.p, id == 'D', key.p, idx.p, status.p);
+  std::vector<double> hk(n);
+  std::vector<int64_t> hi(n);
+  d2h(hk.data(), key.p, n, c.s);
+  CK(cudaMemcpyAsync(hi.data(), idx.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c.s));
+  check_status_dev(c, status.p, "lapack_sort");
+  for (int64_t t = 0; t < n; ++t) {
+    vector[t] = (id == 'D') ? -hk[t] : hk[t];
+    keys[hi[t]] = (int32_t)(t + 1);
   }
-  for (int64_t t = 0; t < n; ++t) vector[t] = (id == 'D') ? -sorted[t] : sorted[t];
   API_END
 }
 
@@ -782,7 +825,7 @@ int dav_free_matmul(int op, int64_t n, int64_t b, const double* array, double* o
   API_BEGIN
   need(array && out && n >= 1 && b >= 1, "bad arguments");
   need(op >= DAV_OP_BENCHMARK_MTX && op <= DAV_OP_TEST_STX, "unknown built-in operator");
-  std::unique_ptr<dav_solver> s(new dav_solver(0, 0, 1, nullptr));
+  std::unique_ptr<dav_solver> s(new dav_solver(default_device(), 0, 1, nullptr));
   s->set_operator(0, n, op);
   DevBuf<double> X, W;
   X.alloc((size_t)n * b); W.alloc((size_t)n * b);
@@ -797,7 +840,7 @@ int dav_compute_on_the_fly(int op, int64_t i, int64_t dim, double* vector) {
   API_BEGIN
   need(vector && dim >= 1 && i >= 1 && i <= dim, "bad arguments");
   need(op >= DAV_OP_BENCHMARK_MTX && op <= DAV_OP_TEST_STX, "unknown built-in operator");
-  std::unique_ptr<dav_solver> s(new dav_solver(0, 0, 1, nullptr));
+  std::unique_ptr<dav_solver> s(new dav_solver(default_device(), 0, 1, nullptr));
   s->set_operator(0, dim, op);
   s->ensure_etab();
   DevBuf<double> col;

@@ -124,6 +124,16 @@ bool pip_small(cudaStream_t s, int mode, int kold, int b, const double* Gall, do
 // Rinv = inverse of the upper triangular R (k x k)
 void invert_upper(cudaStream_t s, int k, const double* R, int64_t ld, double* Rinv);
 
+// ---- densesolve.cu : the remaining lapack_wrapper helpers on the device -----------------------------------------
+// Aaug: n x (n + nrhs) column-major (lda), the right-hand sides behind the matrix; on return the nrhs columns hold the
+// solutions.  Blocked LU with partial pivoting; piv: n ints of scratch; status |= 2 for a singular matrix / NaN.
+void lu_solve(cudaStream_t s, int n, int nrhs, double* Aaug, int64_t lda, int* piv, int* status);
+void transpose(cudaStream_t s, int64_t rows, int64_t cols, const double* in, int64_t ldi, double* out, int64_t ldo);
+// key[0..n) = in sorted ascending (descending: by -in, i.e. descending in), idx = original positions, ties by position
+// (the stable order); key / idx hold sort_pairs_padded(n) entries.  status |= 1 on NaN.
+int64_t sort_pairs_padded(int64_t n);
+void sort_pairs(cudaStream_t s, int64_t n, const double* in, bool descending, double* key, int64_t* idx, int* status);
+
 // ---- vecops.cu : n x k vector-block kernels and generators --------------------------------------
 void fill_zero(cudaStream_t s, double* p, size_t count);
 void copy_matrix(cudaStream_t s, int64_t rows, int64_t cols, const double* src, int64_t lds, double* dst,
@@ -141,6 +151,11 @@ inline size_t topk_scratch_entries(int64_t count, int k) {
 void topk_smallest(cudaStream_t s, const double* diag, const int64_t* gidx /*nullable*/, int64_t count,
                    int64_t row0, int k, double* out_val, int64_t* out_idx, int* status, double* scratch_val,
                    int64_t* scratch_idx);
+// X (n x w, ld n) = columns c0 .. c0 + w of the identity; diag[i - row0] = Y(i - row0, i - c0) for the owned rows of
+// that column range (extract_diagonal_free, davidson.f90:490-523, with the block on the device)
+void unit_block(cudaStream_t s, double* X, int64_t n, int64_t c0, int w);
+void take_diagonal(cudaStream_t s, const double* Y, int64_t ldy, int64_t nl, int64_t row0, int64_t c0, int w,
+                   double* diag);
 // V(nl x k) one-hot: V(idx[j]-row0, j) = 1 when idx[j] is a local row
 void set_onehot(cudaStream_t s, double* V, int64_t ldv, int64_t nl, int64_t row0, const int64_t* idx, int k);
 // out(:, j) = A(:, idx[j])   (A is nl x n local row block)

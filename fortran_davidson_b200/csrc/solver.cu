@@ -206,6 +206,23 @@ void dav_solver::set_callback(int which, int64_t n_, dav_gemv_fn fn, void* ctx, 
   }
 }
 
+void dav_solver::set_device_callback(int which, int64_t n_, dav_device_gemv_fn fn, void* ctx, const double* diag) {
+  CK(cudaSetDevice(device));
+  if (!fn) DAV_THROW(DAV_ERR_INVALID, "null operator callback");
+  clear_matrix(which);
+  set_dims(n_);
+  Matrix& m = mat[which];
+  m.kind = DEVCALLBACK;
+  m.dfn = fn;
+  m.ctx = ctx;
+  m.n = n;
+  if (diag) {
+    m.diag.alloc((size_t)std::max<int64_t>(nl, 1));
+    CK(cudaMemcpy(m.diag.p, diag + row0, (size_t)nl * 8, cudaMemcpyHostToDevice));
+    m.diag_valid = true;
+  }
+}
+
 void dav_solver::download(int which, double* host_rows, int64_t ld) {
   CK(cudaSetDevice(device));
   Matrix& m = mat[which];
@@ -250,6 +267,18 @@ void dav_solver::ensure_diag(int which) {
     }
     CK(cudaMemcpyAsync(m.diag.p, d.data() + row0, (size_t)nl * 8, cudaMemcpyHostToDevice, stream));
     CK(cudaStreamSynchronize(stream));
+  } else if (m.kind == DEVCALLBACK) {
+    // the same extraction with the block staying on the device: unit vectors, 64 at a time
+    const int blk = 64;
+    Xfull.alloc((size_t)n * blk);
+    T.alloc((size_t)std::max<int64_t>(nl, 1) * blk);
+    const int64_t ldy = std::max<int64_t>(nl, 1);
+    for (int64_t c0 = 0; c0 < n; c0 += blk) {
+      const int w = (int)std::min<int64_t>(blk, n - c0);
+      unit_block(stream, Xfull.p, n, c0, w);
+      m.dfn(Xfull.p, n, T.p, ldy, n, w, row0, nl, (void*)stream, m.ctx);
+      take_diagonal(stream, T.p, ldy, nl, row0, c0, w, m.diag.p);
+    }
   }
   m.diag_valid = true;
 }
@@ -374,6 +403,8 @@ void dav_solver::apply_full(int which, const double* Xf, int64_t ldx, int b, dou
     CK(cudaMemcpy2DAsync(W, (size_t)ldw * 8, host_y.data() + row0, (size_t)n * 8, (size_t)nl * 8, (size_t)b,
                          cudaMemcpyHostToDevice, stream));
     CK(cudaStreamSynchronize(stream));
+  } else if (m.kind == DEVCALLBACK) {
+    m.dfn(Xf, ldx, W, ldw, n, b, row0, nl, (void*)stream, m.ctx);
   } else {
     DAV_THROW(DAV_ERR_STATE, "no matrix set in slot %d", which);
   }

@@ -7,7 +7,7 @@
 #include "kernels.cuh"
 
 struct dav_solver {
-  enum Kind { NONE = 0, DENSE = 1, BUILTIN = 2, CALLBACK = 3 };
+  enum Kind { NONE = 0, DENSE = 1, BUILTIN = 2, CALLBACK = 3, DEVCALLBACK = 4 };
   struct Matrix {
     Kind kind = NONE;
     int64_t n = 0;
@@ -17,6 +17,7 @@ struct dav_solver {
     int op = 0;                      // BUILTIN
     dav::FreeTables* ftab = nullptr; // BUILTIN: tables of the tensor-pipe generator (freeops_dmma.cu)
     dav_gemv_fn fn = nullptr;        // CALLBACK
+    dav_device_gemv_fn dfn = nullptr;  // DEVCALLBACK: enqueues on the solver's stream, device pointers
     void* ctx = nullptr;
     dav::DevBuf<double> diag;        // local diagonal entries
     bool diag_valid = false;
@@ -69,6 +70,7 @@ struct dav_solver {
   void upload_rows(int which, int64_t n, const double* host_rows, int64_t ld);
   void set_operator(int which, int64_t n, int op);
   void set_callback(int which, int64_t n, dav_gemv_fn fn, void* ctx, const double* diag);
+  void set_device_callback(int which, int64_t n, dav_device_gemv_fn fn, void* ctx, const double* diag);
   void download(int which, double* host_rows, int64_t ld);
   void ensure_etab();
   void ensure_diag(int which);

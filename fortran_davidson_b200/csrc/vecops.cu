@@ -142,6 +142,24 @@ __global__ void __launch_bounds__(TOPK_CHUNK) rank_select_kernel(const double* _
   (void)final_round;
 }
 
+// X (n x w) = columns c0 .. c0 + w of the identity
+__global__ void unit_block_kernel(double* __restrict__ X, int64_t n, int64_t c0, int w) {
+  const int64_t total = n * w;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = e / n, i = e - j * n;
+    X[e] = (i == c0 + j) ? 1.0 : 0.0;
+  }
+}
+
+// diag[i - row0] = Y(i - row0, i - c0) for the global rows i in [c0, c0 + w) that this rank owns
+__global__ void take_diagonal_kernel(const double* __restrict__ Y, int64_t ldy, int64_t nl, int64_t row0, int64_t c0,
+                                     int w, double* __restrict__ diag) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= w) return;
+  const int64_t i = c0 + j - row0;
+  if (i >= 0 && i < nl) diag[i] = Y[i + (int64_t)j * ldy];
+}
+
 __global__ void set_onehot_kernel(double* V, int64_t ldv, int64_t nl, int64_t row0, const int64_t* idx, int k) {
   for (int j = threadIdx.x; j < k; j += blockDim.x) {
     const int64_t r = idx[j] - row0;
@@ -326,6 +344,19 @@ void topk_smallest(cudaStream_t s, const double* diag, const int64_t* gidx, int6
     cv = ov; ci = oi; m = nch * k; r0 = 0;
     side ^= 1;
   }
+}
+
+void unit_block(cudaStream_t s, double* X, int64_t n, int64_t c0, int w) {
+  if (n <= 0 || w <= 0) return;
+  unit_block_kernel<<<grid1((size_t)n * w), 256, 0, s>>>(X, n, c0, w);
+  LAUNCHED();
+}
+
+void take_diagonal(cudaStream_t s, const double* Y, int64_t ldy, int64_t nl, int64_t row0, int64_t c0, int w,
+                   double* diag) {
+  if (w <= 0) return;
+  take_diagonal_kernel<<<(w + 63) / 64, 64, 0, s>>>(Y, ldy, nl, row0, c0, w, diag);
+  LAUNCHED();
 }
 
 void set_onehot(cudaStream_t s, double* V, int64_t ldv, int64_t nl, int64_t row0, const int64_t* idx, int k) {

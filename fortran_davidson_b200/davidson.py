@@ -6,7 +6,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import GEMV_FN, Stats, check, dp, lib
+from ._lib import DEVICE_GEMV_FN, GEMV_FN, Stats, check, dp, lib
 
 METHODS = {"DPR": 0, "GJD": 1}
 OP_BENCHMARK_MTX, OP_IDENTITY, OP_TEST_MTX, OP_TEST_STX = 0, 1, 2, 3
@@ -161,6 +161,20 @@ class DavidsonSolver:
         self._cbs.append(cb)
         d = np.ascontiguousarray(diag, dtype=np.float64) if diag is not None else None
         check(lib().dav_matrix_set_callback(self._h, C.c_int(which), C.c_int64(n), cb, None, dp(d)))
+        self.n = n
+
+    def set_device_callback(self, which, n, fun, diag=None):
+        """Matrix-free operator as a DEVICE functor: fun(d_x, ldx, d_y, ldy, n, b, row_begin, nrows, stream) gets raw
+        device addresses (ints) and must enqueue on the CUDA stream `stream` the computation of rows
+        [row_begin, row_begin + nrows) of Op * X (see dav_matrix_set_device_callback)."""
+
+        def cb(xp, ldx, yp, ldy, n_, b, r0, nr, stream, _ctx):
+            fun(int(xp or 0), int(ldx), int(yp or 0), int(ldy), int(n_), int(b), int(r0), int(nr), int(stream or 0))
+
+        cfn = DEVICE_GEMV_FN(cb)
+        self._cbs.append(cfn)
+        d = np.ascontiguousarray(diag, dtype=np.float64) if diag is not None else None
+        check(lib().dav_matrix_set_device_callback(self._h, C.c_int(which), C.c_int64(n), cfn, None, dp(d)))
         self.n = n
 
     def clear(self, which):

@@ -60,6 +60,10 @@ const char* dav_last_error(void);
 int dav_version(void);
 /* number of usable CUDA devices (0 without a GPU; never fails) */
 int dav_device_count(void);
+/* GPU used by every call that takes no handle (the drop-in solver calls of section 1 and the array_utils /
+ * lapack_wrapper mirrors of section 3): this call, else the environment variable DAV_DEVICE, else device 0.
+ * device = -1 returns to the environment / default.  (The reference has no notion of a device: davidson.f90:51-83.) */
+int dav_set_default_device(int device);
 
 /* =============================================================================================
  * 1. Drop-in solver calls (host pointers in, host pointers out).
@@ -135,6 +139,19 @@ int dav_matrix_upload_rows(dav_solver_t* h, int which, int64_t n, const double* 
 /* matrix-free: built-in generator or host callback (diag may be NULL) */
 int dav_matrix_set_operator(dav_solver_t* h, int which, int64_t n, int op);
 int dav_matrix_set_callback(dav_solver_t* h, int which, int64_t n, dav_gemv_fn fn, void* ctx, const double* diag);
+/* matrix-free with a DEVICE functor: the generalisation of the reference's fun(i, dim) / fun_matrix_gemv operators
+ * (davidson.f90:317-325, :526-569) that keeps the block on the GPU.  The library calls
+ *     fn(d_x, ldx, d_y, ldy, n, b, row_begin, nrows, cuda_stream, ctx)
+ * with DEVICE pointers: d_x = the complete block X (n x b, column-major, leading dimension ldx), d_y = where the rows
+ * [row_begin, row_begin + nrows) of Op * X go (nrows x b, leading dimension ldy; nrows = this rank's share, = n on
+ * one GPU).  fn must only ENQUEUE work on `cuda_stream` (a cudaStream_t) and return; no host copy, no
+ * synchronisation, any rank count.  diag: the operator's diagonal (host pointer, n entries) or NULL, in which case it
+ * is extracted by applying the functor to unit vectors, 64 at a time, like extract_diagonal_free
+ * (davidson.f90:490-523). */
+typedef void (*dav_device_gemv_fn)(const double* d_x, int64_t ldx, double* d_y, int64_t ldy, int64_t n, int64_t b,
+                                   int64_t row_begin, int64_t nrows, void* cuda_stream, void* ctx);
+int dav_matrix_set_device_callback(dav_solver_t* h, int which, int64_t n, dav_device_gemv_fn fn, void* ctx,
+                                   const double* diag);
 int dav_matrix_clear(dav_solver_t* h, int which);
 /* copy the local row block back (row_end-row_begin rows x n columns, ld >= rows) -- parity tests */
 int dav_matrix_download(dav_solver_t* h, int which, double* host_rows, int64_t ld);
@@ -248,6 +265,8 @@ int dav_generate_diagonal_dominant(int64_t m, double sparsity, const double* dia
 int dav_generate_preconditioner(int64_t n, const double* diag, int dim_sub, double* precond, int64_t ld);
 /* norm (array_utils.f90:46-53) */
 int dav_norm(int64_t n, const double* vector, double* result);
+/* the same as a value (NaN on any error): lets the Fortran shim keep `norm` PURE like array_utils.f90:46 */
+double dav_norm_value(int64_t n, const double* vector);
 /* lapack_generalized_eigensolver (lapack_wrapper.f90:14-91): all eigenpairs ascending, upper
  * triangle read; stx may be NULL.  Device Jacobi. */
 int dav_lapack_generalized_eigensolver(int dim, const double* mtx, const double* stx, double* eigenvalues,

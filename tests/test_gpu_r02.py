@@ -9,6 +9,7 @@ import sys
 
 import numpy as np
 import pytest
+import scipy.linalg as sl
 
 import fortran_davidson_b200 as fd
 from fortran_davidson_b200._lib import check, dp, lib
@@ -236,3 +237,128 @@ def test_sharded_solver_parity_under_torchrun(script):
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert "_CHECK_PASSED world=%d" % ng in p.stdout
+
+
+# ---------------------------------------------------------------- lapack_wrapper mirrors entirely on the device (r02)
+def test_lapack_qr_rank_deficient_basis_never_fails():
+    """DGEQRF + DORGQR (lapack_wrapper.f90:176-236) return an orthonormal basis for any input; the CholeskyQR2 of r01
+    raised on a rank-deficient one.  Now: orthonormal, and it contains the span of the input."""
+    from fortran_davidson_b200 import lapack_wrapper as lw
+    rng = np.random.default_rng(0)
+    m, n = 500, 12
+    X = rng.standard_normal((m, n))
+    X[:, 7] = X[:, 2] - 3.0 * X[:, 5]   # exactly dependent
+    X[:, 10] = 0.0                       # zero column
+    Q = lw.lapack_qr(X)
+    assert np.abs(Q.T @ Q - np.eye(n)).max() < 1e-12
+    resid = X - Q @ (Q.T @ X)
+    assert np.abs(resid).max() < 1e-10 * np.abs(X).max()
+    # full rank: still the QR factor (up to column signs), like the reference
+    Y = rng.standard_normal((m, n))
+    Qy = lw.lapack_qr(Y)
+    Qr, _ = np.linalg.qr(Y)
+    assert np.abs(np.abs(Qy.T @ Qr) - np.eye(n)).max() < 1e-10
+
+
+@pytest.mark.parametrize("n", [1, 7, 33, 300, 2000])
+def test_lapack_solver_device_lu(n):
+    """lapack_solver (DSYSV 'U', lapack_wrapper.f90:238-277) on the device, no size cap: symmetric INDEFINITE systems,
+    only the upper triangle may be read."""
+    from fortran_davidson_b200 import lapack_wrapper as lw
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n))
+    A = (A + A.T) / 2                      # indefinite
+    b = rng.standard_normal(n)
+    junk = np.triu(A) + np.tril(np.full((n, n), 123.0), -1)
+    x = lw.lapack_solver(junk, b)
+    ref = np.linalg.solve(A, b)
+    assert np.abs(A @ x - b).max() <= 1e-10 * max(1.0, np.abs(b).max()) * max(1.0, np.linalg.cond(A) * 1e-3)
+    assert np.abs(x - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max()) * max(1.0, np.linalg.cond(A) * 1e-3)
+
+
+def test_lapack_solver_singular_matrix_is_reported():
+    from fortran_davidson_b200 import lapack_wrapper as lw
+    A = np.ones((5, 5))
+    with pytest.raises(fd.DavidsonError):
+        lw.lapack_solver(np.zeros((4, 4)), np.ones(4))
+    assert A.shape == (5, 5)
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 1000, 1025, 70001])
+def test_lapack_sort_device_bitonic(n):
+    from fortran_davidson_b200 import lapack_wrapper as lw
+    rng = np.random.default_rng(n)
+    v = rng.integers(0, max(2, n // 3), size=n).astype(np.float64)  # many ties
+    for id_ in ("I", "D"):
+        s, keys = lw.lapack_sort(id_, v)
+        ref = np.sort(v) if id_ == "I" else np.sort(v)[::-1]
+        assert np.array_equal(s, ref)
+        assert sorted(keys.tolist()) == list(range(1, n + 1))
+        assert np.array_equal(s[keys - 1], v)      # keys[original position] = rank
+        order = np.argsort(keys)                    # original positions in sorted order: ties keep their order
+        same = s[1:] == s[:-1]
+        assert np.all(order[1:][same] > order[:-1][same])
+
+
+def test_lapack_matmul_transposed_b_on_device():
+    from fortran_davidson_b200 import lapack_wrapper as lw
+    rng = np.random.default_rng(4)
+    A, B = rng.standard_normal((130, 57)), rng.standard_normal((41, 57))
+    out = lw.lapack_matmul("N", "T", A, B, 2.0)
+    assert np.abs(out - 2.0 * A @ B.T).max() < 1e-12 * 57
+    out = lw.lapack_matmul("T", "T", rng.standard_normal((57, 130)), B)
+    assert out.shape == (130, 41)
+
+
+def test_default_device_selection():
+    check(lib().dav_set_default_device(C.c_int(0)))
+    assert lib().dav_set_default_device(C.c_int(lib().dav_device_count())) != 0
+    check(lib().dav_set_default_device(C.c_int(-1)))
+
+
+# ---------------------------------------------------------------- device functor operators (SURVEY 8f-3)
+class _DevView:
+    """Raw device address -> __cuda_array_interface__ (column-major rows x cols view with leading dimension ld)."""
+
+    def __init__(self, ptr, rows, cols, ld):
+        self.__cuda_array_interface__ = {"shape": (rows, cols), "typestr": "<f8", "data": (ptr, False), "version": 3,
+                                         "strides": (8, 8 * ld)}
+
+
+def _torch_functor(torch, Adev):
+    def fun(xp, ldx, yp, ldy, n, b, r0, nr, stream):
+        if nr == 0:
+            return
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream)):
+            x = torch.as_tensor(_DevView(xp, n, b, ldx), device="cuda")
+            y = torch.as_tensor(_DevView(yp, nr, b, ldy), device="cuda")
+            y.copy_(Adev[r0:r0 + nr] @ x)
+    return fun
+
+
+@pytest.mark.parametrize("give_diag", [True, False])
+def test_device_functor_operator_matches_the_dense_solve(give_diag):
+    """A user operator that stays on the GPU (dav_matrix_set_device_callback): here a torch matmul enqueued on the
+    solver's stream.  Same Ritz pairs and iteration count as the host-callback path and as the oracle's
+    matrix-free loop (davidson.f90:277-460: always generalized, DPR, non-sticky convergence)."""
+    import torch
+    n, L = 1500, 4
+    A = orc.generate_diagonal_dominant(n, 1e-2, None, 2)
+    B = orc.generate_diagonal_dominant(n, 1e-3, 1.0, 3)
+    Ad, Bd = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    s = fd.DavidsonSolver()
+    s.set_device_callback(0, n, _torch_functor(torch, Ad), np.diag(A).copy() if give_diag else None)
+    s.set_device_callback(1, n, _torch_functor(torch, Bd), np.diag(B).copy() if give_diag else None)
+    ev, vec, iters = s.solve(L, "DPR", 200, 1e-9, 24)
+    s.close()
+    h = fd.DavidsonSolver()
+    h.set_callback(0, n, lambda x: A @ x, np.diag(A).copy())
+    h.set_callback(1, n, lambda x: B @ x, np.diag(B).copy())
+    ev2, vec2, iters2 = h.solve(L, "DPR", 200, 1e-9, 24)
+    h.close()
+    assert iters == iters2
+    assert np.abs(ev - ev2).max() / np.abs(ev2).max() < 1e-12
+    es = sl.eigh(A, b=B, eigvals_only=True)[:L]
+    assert np.abs(ev - es).max() / np.abs(es).max() < EV_RTOL
+    for j in range(L):
+        assert np.linalg.norm(A @ vec[:, j] - ev[j] * (B @ vec[:, j])) < 1e-8
