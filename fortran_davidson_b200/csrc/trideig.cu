@@ -501,15 +501,21 @@ __global__ void __launch_bounds__(256 * TS / TSR) tridiag_reg_kernel(int k, cons
 }
 
 // ---- 2. one warp per eigenpair ----------------------------------------------------------------------------------
-constexpr int EW = 8;  // warps per CTA
+// warps per CTA.  r02: 4 instead of 8 -- the Sturm / twisted recurrences are chains of FP64 instructions, one warp
+// issues one every ~4 cycles, and two such warps per scheduler already halve each other's speed (k = 128: 16 -> 32 CTAs)
+constexpr int EW = 4;
 
 template <int KT>  // rows per lane: k <= 32 * KT
 __global__ void __launch_bounds__(EW * 32) tri_eigvec_kernel(int k, const double* __restrict__ d_in,
                                                             const double* __restrict__ e_in,
                                                             const double* __restrict__ Vh,
                                                             const double* __restrict__ tau, double* __restrict__ Y,
-                                                            double* __restrict__ lam_out, int vh_smem) {
+                                                            double* __restrict__ lam_out, int vh_smem,
+                                                            double* prof) {
   extern __shared__ __align__(16) double sm[];
+#ifdef DAV_TRIDIAG_PROFILE
+  long long pt0 = clock64(), pt1 = 0, pt2 = 0, pt3 = 0;
+#endif
   // T is scaled to unit norm (ds = d / tn, es = e / tn): counts and eigenvectors are scale invariant, and the
   // characteristic-polynomial recurrence below can then grow by at most 3x per step
   double* ds = sm;           // k
@@ -586,7 +592,11 @@ __global__ void __launch_bounds__(EW * 32) tri_eigvec_kernel(int k, const double
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const double pn = fma(dc[q] - x, pc, -(ec[q] * pm));
-        const bool nneg = (pn == 0.0) ? !neg : (pn < 0.0);
+        // sign tests on the integer pipe (the FP64 pipe is what this loop is bound by): a zero takes the sign
+        // opposite to its predecessor (NaN input is caught by the guard, whatever it counts as here)
+        const int hi = __double2hiint(pn);
+        const bool zero = ((hi & 0x7fffffff) | __double2loint(pn)) == 0;
+        const bool nneg = zero ? !neg : (hi < 0);
         cnt += nneg != neg;
         neg = nneg;
         pm = pc;
@@ -615,6 +625,9 @@ __global__ void __launch_bounds__(EW * 32) tri_eigvec_kernel(int k, const double
     if (first > 0) lo = xlo;
   }
   const double lam = 0.5 * (lo + hi);  // scaled
+#ifdef DAV_TRIDIAG_PROFILE
+  pt1 = clock64();
+#endif
 
   // ---- eigenvector of T: twisted factorisation.  Lane 0 runs the forward sequence (top down), lane 1 the backward
   // one (bottom up), one instruction stream for both.  The pivots q_i = p_i / p_{i-1} are NOT formed inside the
@@ -700,11 +713,17 @@ __global__ void __launch_bounds__(EW * 32) tri_eigvec_kernel(int k, const double
 #pragma unroll
   for (int t = 0; t < KT; ++t) zr[t] *= inv;
 
+#ifdef DAV_TRIDIAG_PROFILE
+  pt2 = clock64();
+#endif
   // ---- back-transformation y = H_0 H_1 ... H_{k-3} z, reflectors applied last to first
   if (vh_smem) {
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
   }
+#ifdef DAV_TRIDIAG_PROFILE
+  pt3 = clock64();
+#endif
   const double* VhP = vh_smem ? vhs : Vh;
   double vc[KT], vn[KT];
   int jj = k - 3;
@@ -730,6 +749,12 @@ __global__ void __launch_bounds__(EW * 32) tri_eigvec_kernel(int k, const double
       vc[t] = vn[t];
     }
   }
+#ifdef DAV_TRIDIAG_PROFILE
+  if (prof && blockIdx.x == gridDim.x / 2 && threadIdx.x == 0) {
+    const long long pt4 = clock64();
+    prof[0] = (double)(pt1 - pt0); prof[1] = (double)(pt2 - pt1); prof[2] = (double)(pt3 - pt2); prof[3] = (double)(pt4 - pt3);
+  }
+#endif
   if (!valid) return;
 #pragma unroll
   for (int t = 0; t < KT; ++t) {
@@ -1128,13 +1153,15 @@ void sym_eigh(cudaStream_t s, int k, double* S, double* Y, double* w, double* sc
   {
     const int grid = (k + EW - 1) / EW;
     size_t sm = (3 + 5 * (size_t)EW) * k * sizeof(double);
+    static const int eprof_on = env_int("DAV_EIGVEC_PROFILE", 0);
+    double* eprof = eprof_on ? flagv + 3 : nullptr;  // (overwrites the tridiagonalisation's profile slots)
     static const int vhs_env = env_int("DAV_EIGVEC_VH_SMEM", 1);
     const int vh_smem = (vhs_env != 0 && sm + kk * sizeof(double) <= (size_t)max_smem) ? 1 : 0;
     if (vh_smem) sm += kk * sizeof(double);
-    if (k <= 64) tri_eigvec_kernel<2><<<grid, EW * 32, sm, s>>>(k, d, e, Vh, tau, Yraw, lam, vh_smem);
-    else if (k <= 128) tri_eigvec_kernel<4><<<grid, EW * 32, sm, s>>>(k, d, e, Vh, tau, Yraw, lam, vh_smem);
-    else if (k <= 256) tri_eigvec_kernel<8><<<grid, EW * 32, sm, s>>>(k, d, e, Vh, tau, Yraw, lam, vh_smem);
-    else tri_eigvec_kernel<16><<<grid, EW * 32, sm, s>>>(k, d, e, Vh, tau, Yraw, lam, vh_smem);
+    if (k <= 64) tri_eigvec_kernel<2><<<grid, EW * 32, sm, s>>>(k, d, e, Vh, tau, Yraw, lam, vh_smem, eprof);
+    else if (k <= 128) tri_eigvec_kernel<4><<<grid, EW * 32, sm, s>>>(k, d, e, Vh, tau, Yraw, lam, vh_smem, eprof);
+    else if (k <= 256) tri_eigvec_kernel<8><<<grid, EW * 32, sm, s>>>(k, d, e, Vh, tau, Yraw, lam, vh_smem, eprof);
+    else tri_eigvec_kernel<16><<<grid, EW * 32, sm, s>>>(k, d, e, Vh, tau, Yraw, lam, vh_smem, eprof);
     CK_LAUNCH();
     ++g_kernel_launches;
   }
