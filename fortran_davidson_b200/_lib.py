@@ -22,7 +22,7 @@ SYMBOLS = [
     "dav_create", "dav_create_distributed", "dav_destroy", "dav_alloc_pinned", "dav_free_pinned", "dav_partition_rows",
     "dav_matrix_generate_diagonal_dominant", "dav_matrix_upload", "dav_matrix_upload_rows",
     "dav_matrix_set_operator",
-    "dav_matrix_set_callback", "dav_matrix_set_device_callback", "dav_matrix_clear", "dav_matrix_download", "dav_solve", "dav_solve_local", "dav_get_stats",
+    "dav_matrix_set_callback", "dav_matrix_set_device_callback", "dav_matrix_clear", "dav_matrix_download", "dav_solve", "dav_solve_local", "dav_get_stats", "dav_set_profiling",
     "dav_set_matvec_impl", "dav_block_matvec", "dav_bench_block_matvec", "dav_generate_diagonal_dominant",
     "dav_generate_preconditioner", "dav_norm", "dav_norm_value", "dav_lapack_generalized_eigensolver",
     "dav_lapack_generalized_eigensolver_lowest", "dav_sym_eigh_info", "dav_lapack_qr", "dav_lapack_solver", "dav_lapack_matmul",

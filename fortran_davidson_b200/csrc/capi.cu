@@ -298,6 +298,13 @@ int dav_matrix_set_device_callback(dav_solver_t* h, int which, int64_t n, dav_de
   API_END
 }
 
+int dav_set_profiling(dav_solver_t* h, int per_phase_spans) {
+  API_BEGIN
+  need(h, "bad handle");
+  h->profile_spans = per_phase_spans != 0;
+  API_END
+}
+
 int dav_matrix_clear(dav_solver_t* h, int which) {
   API_BEGIN
   need(h && (which == 0 || which == 1), "bad handle / slot");

@@ -32,6 +32,7 @@ using namespace dav;
 namespace {
 enum { SPAN_MATVEC = 0, SPAN_RR = 1, SPAN_ORTH = 2, SPAN_RESID = 3, SPAN_PROJ = 4, SPAN_INIT = 5, SPAN_TOTAL = 6,
        SPAN_GATHER = 7, SPAN_OUT = 8, SPAN_COMM = 9 };
+constexpr int CONV_HOST_MAX = 2032;  // residual norms that fit the page-locked flag block
 constexpr int EV_POOL = 1 << 16;  // events; beyond it spans are dropped and counted (stats.spans_dropped)
 }  // namespace
 
@@ -53,7 +54,7 @@ dav_solver::dav_solver(int device_, int rank, int world, const void* id128) : de
   comm.init(rank, world, id128);
   CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&pip_flags_ev, cudaEventDisableTiming));
-  CK(cudaMallocHost((void**)&pip_flags_host, 8 * sizeof(double)));
+  CK(cudaMallocHost((void**)&pip_flags_host, (16 + CONV_HOST_MAX) * sizeof(double)));
   std::memset(&stats, 0, sizeof(stats));
 }
 
@@ -295,9 +296,11 @@ void dav_solver::ensure_plan(int which, int max_b) {
 }
 
 int dav_solver::begin_span(int kind) {
-  // DAV_NO_SPANS=1: only the total is timed (the per-phase events cost two cudaEventRecord calls per span)
-  static const bool no_spans = [] { const char* e = std::getenv("DAV_NO_SPANS"); return e && std::atoi(e) != 0; }();
-  if (no_spans && kind != SPAN_TOTAL) return -1;
+  // Per-phase spans are OFF unless asked for (dav_set_profiling / DAV_SPANS=1): ~80 event records per solve cost
+  // 0.12 ms of the 2.2 ms a rank of 8 spends outside the block matvec (profiles/r02: 2.249 -> 2.133 ms).  The total
+  // (dav_stats_t.solve_ms) is always timed.
+  static const bool env_spans = [] { const char* e = std::getenv("DAV_SPANS"); return e && std::atoi(e) != 0; }();
+  if (!(profile_spans || env_spans) && kind != SPAN_TOTAL) return -1;
   if (ev_used + 2 > (int)ev_pool.size()) {
     if ((int)ev_pool.size() >= EV_POOL) {
       stats.spans_dropped += 1;
@@ -499,7 +502,8 @@ void dav_solver::alloc_work(int lowest, int kcap_) {
 }
 
 void dav_solver::check_status(const char* where) {
-  int h = 0;
+  // page-locked landing zone: a copy to pageable memory is staged and blocks the host before the stream is drained
+  int& h = *reinterpret_cast<int*>(pip_flags_host + 8);
   CK(cudaMemcpyAsync(&h, status.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
   CK(cudaStreamSynchronize(stream));
   if (h & 2)
@@ -780,8 +784,10 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
     };
     residual_cols(0, L);
     end_span(sp);
-    CK(cudaMemcpyAsync(hn2.data(), norms2.p, (size_t)L * 8, cudaMemcpyDeviceToHost, stream));
+    double* hn2p = L <= CONV_HOST_MAX ? pip_flags_host + 16 : hn2.data();  // page-locked when it fits
+    CK(cudaMemcpyAsync(hn2p, norms2.p, (size_t)L * 8, cudaMemcpyDeviceToHost, stream));
     check_status("Rayleigh-Ritz");  // synchronises the stream
+    if (hn2p != hn2.data()) std::memcpy(hn2.data(), hn2p, (size_t)L * 8);
     // step 4.2 (davidson.f90:173-178; free :412-416)
     double max_err = 0.0;
     bool all_now = true;

@@ -32,6 +32,7 @@ struct dav_solver {
   std::vector<double> etab_host;
   int matvec_impl = DAV_MATVEC_AUTO;
   bool local_vectors = false;  // dav_solve_local: Ritz vectors returned row-sharded
+  bool profile_spans = false;  // dav_set_profiling: per-phase event spans (the *_ms fields of dav_stats_t)
   dav_stats_t stats;
 
   // ---- work space of a solve

@@ -234,6 +234,10 @@ class DavidsonSolver:
                               C.byref(iters)))
         return ev, vec, (iters.value if iters.value >= 0 else None)
 
+    def set_profiling(self, per_phase_spans):
+        """Per-phase event spans of the following solves (Stats.matvec_ms, rr_ms, ...); off by default."""
+        check(lib().dav_set_profiling(self._h, C.c_int(1 if per_phase_spans else 0)))
+
     def stats(self):
         s = Stats()
         check(lib().dav_get_stats(self._h, C.byref(s)))

@@ -191,6 +191,10 @@ typedef struct {
   int pip_fallbacks;        /* expansion blocks whose fast orthonormalisation was rejected and redone by the SVQB loop */
 } dav_stats_t;
 int dav_get_stats(dav_solver_t* h, dav_stats_t* out);
+/* per_phase_spans != 0: the following solves also time every phase with CUDA events (matvec_ms, rr_ms, orth_ms, ...,
+ * comm_ms of dav_stats_t; ~80 event records per solve, ~0.1 ms).  Default 0: only solve_ms is timed, the per-phase
+ * fields stay 0.  The environment variable DAV_SPANS=1 switches the spans on for every handle. */
+int dav_set_profiling(dav_solver_t* h, int per_phase_spans);
 
 /* knobs: DAV_MATVEC_* implementation of the block matvec */
 int dav_set_matvec_impl(dav_solver_t* h, int impl);
