@@ -89,7 +89,8 @@ void jacobi_eigh(cudaStream_t s, int k, double* S, double* Y, double* w, double*
 // factorisation, back-transformation) + a-posteriori guard; Jacobi when the guard rejects or k is small.
 // scratch: >= sym_eigh_scratch_doubles(k).
 size_t sym_eigh_scratch_doubles(int k);
-void sym_eigh(cudaStream_t s, int k, double* S, double* Y, double* w, double* scratch, int* status);
+// lds: leading dimension of S (0 = k); a strided S is accepted for k >= 16 (the fast path copies it anyway)
+void sym_eigh(cudaStream_t s, int k, double* S, double* Y, double* w, double* scratch, int* status, int64_t lds = 0);
 bool sym_eigh_uses_tridiag(int k);
 // guard outputs of the last sym_eigh call on this scratch: double[8] {max|S|, max|G-I|, max residual} + int accept
 double* sym_eigh_flags(double* scratch, int k);

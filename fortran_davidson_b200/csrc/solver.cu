@@ -515,6 +515,11 @@ void dav_solver::check_status(const char* where) {
 // Generalized: Bp = U S U^T, Tm = U S^-1/2, (Tm^T Ap Tm) Z = Z theta, Y = Tm Z  => Y^T Bp Y = I like DSYGV itype=1.
 void dav_solver::rayleigh_ritz(int k, bool gev) {
   const int sp = begin_span(SPAN_RR);
+  if (!gev && sym_eigh_uses_tridiag(k)) {
+    sym_eigh(stream, k, Ap.p, Y.p, theta.p, jscratch.p, status.p, kcap);  // reads the projection in place
+    end_span(sp);
+    return;
+  }
   copy_matrix(stream, k, k, Ap.p, kcap, S1.p, k);
   if (!gev) {
     sym_eigh(stream, k, S1.p, Y.p, theta.p, jscratch.p, status.p);
@@ -613,8 +618,9 @@ void dav_solver::orthonormalize_block(double* Cblk, int b, int kold, double* des
   end_span(sp);
 }
 
-// Fast path of the block orthonormalisation: the new block sits in V(:, kold : kold+b), i.e. [V | C] is ONE
-// contiguous nl x (kold+b) array.  Two passes of block classical Gram-Schmidt with the Pythagorean inner product
+// Fast path of the block orthonormalisation.  The new block comes from C (where the residual kernel wrote the
+// corrections) and ends in V(:, kold : kold+b); [V | C] and [V | T] are two-block operands of the tall-skinny products
+// (r01: one contiguous nl x (kold+b) array after a copy).  Two passes of block classical Gram-Schmidt with the Pythagorean inner product
 // (BCGS-PIP2): per pass ONE tall-skinny product [V C]^T C (projection coefficients H and Gram matrix together, one
 // all-reduce), the small factorisation G' = C^T C - H^T H = R^T R on one CTA, and ONE tall-skinny update
 // C <- [V C] [-H R^-1; R^-1].  No host round trip until the flags of both passes are read once, before the last
@@ -639,10 +645,19 @@ bool dav_solver::orthonormalize_block_pip(int b, int kold) {
   const bool two_block = kold % 4 == 0;
   const GemmSplit vt{T.p, ldv, kold};
   // pass 1: [V C]^T C in one product (split-K partials summed over K and over the ranks by one kernel),
-  // C1 = [V C] M -> T
-  tn_reduce(kb, b, V.p, Vnew, gemm_ws, dav::ReduceOut{0, G.p, kb, 0});
-  small_ops(0);
-  gemm(stream, false, nl, b, kb, 1.0, V.p, ldv, Z.p, kb, 0.0, T.p, ldv, nullptr, 0);
+  // C1 = [V C] M -> T.  The corrections are read where the residual kernel left them (C): [V | C] is a two-block
+  // operand, no copy behind the basis (r01 copied C to V(:, kold:) first).
+  if (two_block) {
+    const GemmSplit vc{C.p, ldv, kold};
+    tn_reduce(kb, b, V.p, C.p, gemm_ws, dav::ReduceOut{0, G.p, kb, 0}, &vc);
+    small_ops(0);
+    gemm(stream, false, nl, b, kb, 1.0, V.p, ldv, Z.p, kb, 0.0, T.p, ldv, nullptr, 0, nullptr, &vc);
+  } else {
+    copy_matrix(stream, nl, b, C.p, ldv, Vnew, ldv);  // [V | C] contiguous
+    tn_reduce(kb, b, V.p, Vnew, gemm_ws, dav::ReduceOut{0, G.p, kb, 0});
+    small_ops(0);
+    gemm(stream, false, nl, b, kb, 1.0, V.p, ldv, Z.p, kb, 0.0, T.p, ldv, nullptr, 0);
+  }
   // pass 2: H = V^T C1 and C1^T C1 into the rows 0..kold / kold.. of the same block
   if (two_block) {
     tn_reduce(kb, b, V.p, T.p, gemm_ws, dav::ReduceOut{0, G.p, kb, 0}, &vt);
@@ -849,9 +864,11 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
                   (long long)n);
       if (method == DAV_METHOD_GJD) gjd_correction(k, gev, tolerance);  // C <- GJD corrections
       double* Q = V.p + (size_t)k * ldv;
-      copy_matrix(stream, nl, k, C.p, ldv, Q, ldv);                   // [V | C] contiguous
-      const bool pip = orthonormalize_block_pip(k, k);                // steps 6-7 (:210-213), enqueued
-      if (!pip) orthonormalize_block(Q, k, k, Q);
+      const bool pip = orthonormalize_block_pip(k, k);                // steps 6-7 (:210-213), enqueued; reads C
+      if (!pip) {
+        copy_matrix(stream, nl, k, C.p, ldv, Q, ldv);
+        orthonormalize_block(Q, k, k, Q);
+      }
       auto expand = [&]() {
         apply_both(Q, k, AV.p + (size_t)k * ldv, gev ? BV.p + (size_t)k * ldv : nullptr);  // the block matvec(s)
         for (int w = 0; w < (gev ? 2 : 1); ++w) project_new_block(w, k, k);

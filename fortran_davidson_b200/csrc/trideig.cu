@@ -71,7 +71,7 @@ __device__ __forceinline__ void make_reflector(int k, int ld, int jn, const doub
 }
 
 template <int RB>  // row blocks of 32 kept in registers during the rank-2 update
-__global__ void __launch_bounds__(1024) tridiag_kernel(int k, const double* __restrict__ S_in, double* gS,
+__global__ void __launch_bounds__(1024) tridiag_kernel(int k, const double* __restrict__ S_in, int64_t lds_in, double* gS,
                                                        int s_in_smem, double* __restrict__ Sfull,
                                                        double* __restrict__ Vh, double* __restrict__ tau,
                                                        double* __restrict__ d, double* __restrict__ e,
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(1024) tridiag_kernel(int k, const double* __re
   double mx = 0.0;
   for (int idx = tid; idx < k * k; idx += nt) {
     const int i = idx % k, j = idx / k;
-    const double x = (i <= j) ? S_in[i + (size_t)j * k] : S_in[j + (size_t)i * k];
+    const double x = (i <= j) ? S_in[i + (size_t)j * lds_in] : S_in[j + (size_t)i * lds_in];
     S[i + (size_t)j * ld] = x;
     Sfull[idx] = x;
     Vh[idx] = 0.0;
@@ -288,7 +288,7 @@ __device__ __forceinline__ double allreduce16(double x) {
 }
 
 template <int TSR, int TS>  // tile = TSR rows x TS columns; 16 TS / TSR x 16 threads
-__global__ void __launch_bounds__(256 * TS / TSR) tridiag_reg_kernel(int k, const double* __restrict__ S_in,
+__global__ void __launch_bounds__(256 * TS / TSR) tridiag_reg_kernel(int k, const double* __restrict__ S_in, int64_t lds_in,
                                                           double* __restrict__ Sfull, double* __restrict__ Vh,
                                                           double* __restrict__ tau, double* __restrict__ d,
                                                           double* __restrict__ e, double* __restrict__ scal) {
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(256 * TS / TSR) tridiag_reg_kernel(int k, cons
       const int a = r0 + i, c = col(jj);
       double x = 0.0;
       if (a < k && c < k) {
-        x = S_in[min(a, c) + (size_t)max(a, c) * k];  // DSYEV 'U': only the upper triangle is read
+        x = S_in[min(a, c) + (size_t)max(a, c) * lds_in];  // DSYEV 'U': only the upper triangle is read
         // the symmetrised copy for the guard, written at the MIRRORED position: the 16 lanes of a tile row then
         // store 256 contiguous bytes (entry (c, a) = entry (a, c))
         Sfull[c + (size_t)a * k] = x;
@@ -1094,9 +1094,11 @@ bool sym_eigh_uses_tridiag(int k) {
   return k >= min_k && k <= 512;
 }
 
-void sym_eigh(cudaStream_t s, int k, double* S, double* Y, double* w, double* scratch, int* status) {
+void sym_eigh(cudaStream_t s, int k, double* S, double* Y, double* w, double* scratch, int* status, int64_t lds) {
   if (k <= 0) return;
+  if (lds <= 0) lds = k;
   if (!sym_eigh_uses_tridiag(k)) {
+    if (lds != k) DAV_THROW(DAV_ERR_INVALID, "sym_eigh: a strided input needs the tridiagonal path (k >= 16)");
     jacobi_eigh(s, k, S, Y, w, scratch, status, nullptr);
     return;
   }
@@ -1129,11 +1131,11 @@ void sym_eigh(cudaStream_t s, int k, double* S, double* Y, double* w, double* sc
     // (16 warps for k > 32: one warp issues a DFMA only every ~4 cycles, so the FP64 pipe of the SM needs >= 4
     // warps per scheduler; DAV_TRIDIAG_WARPS=8 selects the 8-warp tiling)
     static const int w8 = env_int("DAV_TRIDIAG_WARPS", 16) == 8;
-    if (k <= 32) tridiag_reg_kernel<2, 2><<<1, 256, 0, s>>>(k, S, Sfull, Vh, tau, d, e, flagv);
-    else if (k <= 64 && w8) tridiag_reg_kernel<4, 4><<<1, 256, 0, s>>>(k, S, Sfull, Vh, tau, d, e, flagv);
-    else if (k <= 64) tridiag_reg_kernel<2, 4><<<1, 512, 0, s>>>(k, S, Sfull, Vh, tau, d, e, flagv);
-    else if (w8) tridiag_reg_kernel<8, 8><<<1, 256, 0, s>>>(k, S, Sfull, Vh, tau, d, e, flagv);
-    else tridiag_reg_kernel<4, 8><<<1, 512, 0, s>>>(k, S, Sfull, Vh, tau, d, e, flagv);
+    if (k <= 32) tridiag_reg_kernel<2, 2><<<1, 256, 0, s>>>(k, S, lds, Sfull, Vh, tau, d, e, flagv);
+    else if (k <= 64 && w8) tridiag_reg_kernel<4, 4><<<1, 256, 0, s>>>(k, S, lds, Sfull, Vh, tau, d, e, flagv);
+    else if (k <= 64) tridiag_reg_kernel<2, 4><<<1, 512, 0, s>>>(k, S, lds, Sfull, Vh, tau, d, e, flagv);
+    else if (w8) tridiag_reg_kernel<8, 8><<<1, 256, 0, s>>>(k, S, lds, Sfull, Vh, tau, d, e, flagv);
+    else tridiag_reg_kernel<4, 8><<<1, 512, 0, s>>>(k, S, lds, Sfull, Vh, tau, d, e, flagv);
   } else {
     // the step loop is instruction-issue bound on per-warp bookkeeping, not on the m^2 FMAs: few warps for small k
     static const int thr_env = env_int("DAV_TRIDIAG_THREADS", 0);
@@ -1144,9 +1146,9 @@ void sym_eigh(cudaStream_t s, int k, double* S, double* Y, double* w, double* sc
     const size_t need_in = (small + kk) * sizeof(double);
     const int s_in = need_in <= (size_t)max_smem - 2048 ? 1 : 0;  // 2 KB of static tables
     const size_t tsm = s_in ? need_in : small * sizeof(double);
-    if (k <= 64) tridiag_kernel<2><<<1, threads, tsm, s>>>(k, S, work, s_in, Sfull, Vh, tau, d, e, flagv);
-    else if (k <= 160) tridiag_kernel<5><<<1, threads, tsm, s>>>(k, S, work, s_in, Sfull, Vh, tau, d, e, flagv);
-    else tridiag_kernel<8><<<1, threads, tsm, s>>>(k, S, work, s_in, Sfull, Vh, tau, d, e, flagv);
+    if (k <= 64) tridiag_kernel<2><<<1, threads, tsm, s>>>(k, S, lds, work, s_in, Sfull, Vh, tau, d, e, flagv);
+    else if (k <= 160) tridiag_kernel<5><<<1, threads, tsm, s>>>(k, S, lds, work, s_in, Sfull, Vh, tau, d, e, flagv);
+    else tridiag_kernel<8><<<1, threads, tsm, s>>>(k, S, lds, work, s_in, Sfull, Vh, tau, d, e, flagv);
   }
   CK_LAUNCH();
   ++g_kernel_launches;
@@ -1188,7 +1190,8 @@ void sym_eigh(cudaStream_t s, int k, double* S, double* Y, double* w, double* sc
     ++g_kernel_launches;
   }
   // Jacobi runs only when the guard rejected the fast path (device-side decision)
-  jacobi_eigh(s, k, S, Y, w, scratch, status, accept);
+  // (from the symmetrised dense copy: the caller's matrix may be strided)
+  jacobi_eigh(s, k, Sfull, Y, w, scratch, status, accept);
 }
 
 }  // namespace dav
