@@ -111,10 +111,12 @@ def measured_peaks():
 
 def measured_traffic(args, b):
     """dram__bytes_read.sum + dram__bytes_write.sum of the matvec kernel per launch from the committed ncu capture
-    (profiles/r01_matvec_traffic.json); only for the exact shape that was captured (n, 1 GPU, dense)."""
+    (profiles/r02_matvec_traffic.json); only for the exact shape that was captured (n, 1 GPU, dense)."""
     if args.free or args.gpus != 1:
         return None
-    p = os.path.join(ROOT, "profiles", "r01_matvec_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02_matvec_traffic.json")
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "r01_matvec_traffic.json")
     if not os.path.exists(p):
         return None
     d = json.load(open(p))

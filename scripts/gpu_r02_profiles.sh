@@ -22,7 +22,12 @@ grep "matvec_kernel\|dram__\|gpu__time" $O/r02_ncu_matvec_dram_$TAG.log | sed 's
 step "ncu full: b = 64 matvec"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:matvec_kernel -c 1 -o $O/r02_ncu_full_matvec_b64_$TAG -f \
   python scripts/matvec_only.py --n 100000 --widths 64 > $O/r02_ncu_full_matvec_b64_$TAG.log 2>&1; echo "rc=$?" | tee -a $O/r02_profiles_steps.log
-step "ncu full: the small kernels of one solve at the 8-GPU shard shape (n = 12500)"
-timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:resid_dmma|pip_small|tridiag_reg|tri_eigvec|guard_cols|gemm_dmma|ll_reduce|fixup|rank_select' -s 70 -c 70 \
-  -o $O/r02_ncu_full_small_kernels_n12500_$TAG -f python bench.py --n 12500 --steps 1 --warmup 1 --no-e2e --no-cpu > $O/r02_ncu_full_small_$TAG.log 2>&1; echo "rc=$?" | tee -a $O/r02_profiles_steps.log
+step "ncu full: the small kernels of one solve at the 8-GPU shard shape (n = 12500), text summary only"
+timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:resid_dmma|pip_small|tridiag_reg|tri_eigvec|guard_cols|gemm_dmma|ll_reduce' -s 20 -c 24 \
+  -o /tmp/r02_small -f python bench.py --n 12500 --steps 1 --warmup 1 --no-e2e --no-cpu > $O/r02_ncu_full_small_$TAG.log 2>&1; echo "rc=$?" | tee -a $O/r02_profiles_steps.log
+ncu -i /tmp/r02_small.ncu-rep --page raw --csv > /tmp/r02_small.csv 2>/dev/null
+python scripts/ncu_pick.py /tmp/r02_small.csv > $O/r02_ncu_full_small_kernels_n12500_$TAG.txt 2>&1
+ncu -i $O/r02_ncu_full_matvec_b64_$TAG.ncu-rep --page raw --csv > /tmp/r02_mv.csv 2>/dev/null
+python scripts/ncu_pick.py /tmp/r02_mv.csv > $O/r02_ncu_full_matvec_b64_$TAG.txt 2>&1
+rm -f $O/r02_ncu_full_matvec_b64_$TAG.ncu-rep
 step "done"
