@@ -270,6 +270,10 @@ class Ctx:
             raise SystemExit("--gpus %d does not match WORLD_SIZE %d" % (args.gpus, self.world))
         torch.cuda.set_device(self.local_rank)
         self.distributed = self.world > 1
+        self.cpu_affinity = None
+        if self.distributed:
+            from fortran_davidson_b200.dist import bind_cpu_to_gpu
+            self.cpu_affinity = bind_cpu_to_gpu(self.local_rank)
         if self.distributed:
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
             ids = [fd.DavidsonSolver.unique_id() if self.rank == 0 else None]
@@ -341,6 +345,7 @@ def timed_solves(cx, w, steps, warmup):
     # one more, untimed, solve with the per-phase event spans switched on: the phase table and the matvec share of the
     # report (the spans cost ~0.1 ms per solve, so the timed solves run without them)
     s.set_profiling(True)
+    cx.barrier()  # (the ranks enter together: otherwise the first exchange of this solve shows their skew)
     s.solve(w.lowest, w.method, 1000, w.tol, md, **kw)
     st = s.stats()
     s.set_profiling(False)

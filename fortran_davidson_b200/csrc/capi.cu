@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <vector>
 
 #include "solver.cuh"
@@ -49,6 +50,14 @@ void need(bool cond, const char* what) {
 // Device of the calls that take no handle (the drop-in solver calls and the lapack_wrapper / array_utils mirrors):
 // dav_set_default_device(), else the environment variable DAV_DEVICE, else device 0.
 int g_default_device = -1;
+std::mutex g_dropin_mu;
+// cached handle of dav_generalized_eigensolver_dense; a raw pointer on purpose: it is never destroyed by a static
+// destructor (CUDA calls after the runtime has shut down), only by dav_release_cache() or an error
+dav_solver* g_dropin = nullptr;
+void drop_cached_handle() {
+  delete g_dropin;
+  g_dropin = nullptr;
+}
 int default_device() {
   if (g_default_device >= 0) return g_default_device;
   const char* e = std::getenv("DAV_DEVICE");
@@ -529,10 +538,42 @@ int dav_generalized_eigensolver_dense(int64_t n, const double* matrix, int64_t l
   API_BEGIN
   need(matrix && eigenvalues && eigenvectors && iters, "NULL argument");
   const int m = parse_method(method);
-  std::unique_ptr<dav_solver> s(new dav_solver(default_device(), 0, 1, nullptr));
-  s->upload(0, n, matrix, lda);
-  if (second_matrix) s->upload(1, n, second_matrix, ldb);
-  s->solve(lowest, m, max_iterations, tolerance, max_dim_sub, eigenvalues, eigenvectors, ldv, iters);
+  // One cached handle per process serves the drop-in calls: a caller that diagonalises a matrix of the same size again
+  // and again (the reference's use inside SCF / BSE loops) reuses the device block of the matrix, its TMA plan, the
+  // workspace and the page-locked staging instead of cudaMalloc + cudaFree of n^2 doubles per call.
+  // dav_release_cache() frees it; DAV_DROPIN_CACHE=0 restores one handle per call.
+  static const bool use_cache = [] { const char* e = std::getenv("DAV_DROPIN_CACHE"); return !(e && std::atoi(e) == 0); }();
+  std::unique_lock<std::mutex> lock(g_dropin_mu);
+  std::unique_ptr<dav_solver> local;
+  dav_solver* s = nullptr;
+  if (use_cache) {
+    if (g_dropin && g_dropin->device != default_device()) drop_cached_handle();
+    if (!g_dropin) g_dropin = new dav_solver(default_device(), 0, 1, nullptr);
+    s = g_dropin;
+  } else {
+    local.reset(new dav_solver(default_device(), 0, 1, nullptr));
+    s = local.get();
+  }
+  try {
+    if (s->n != n) {  // another problem size: start from a clean handle state
+      s->clear_matrix(0);
+      s->clear_matrix(1);
+    }
+    s->upload(0, n, matrix, lda);
+    if (second_matrix) s->upload(1, n, second_matrix, ldb);
+    else s->clear_matrix(1);
+    s->solve(lowest, m, max_iterations, tolerance, max_dim_sub, eigenvalues, eigenvectors, ldv, iters);
+  } catch (...) {
+    if (use_cache) drop_cached_handle();  // unknown state after an error
+    throw;
+  }
+  API_END
+}
+
+int dav_release_cache(void) {
+  API_BEGIN
+  std::unique_lock<std::mutex> lock(g_dropin_mu);
+  drop_cached_handle();
   API_END
 }
 

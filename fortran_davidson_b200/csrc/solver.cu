@@ -154,11 +154,17 @@ void dav_solver::generate_diagonal_dominant(int which, int64_t n_, double sparsi
 void dav_solver::upload(int which, int64_t n_, const double* host, int64_t ld) {
   CK(cudaSetDevice(device));
   if (!host || ld < n_) DAV_THROW(DAV_ERR_INVALID, "upload: bad host matrix / leading dimension");
-  clear_matrix(which);
-  set_dims(n_);
   Matrix& m = mat[which];
-  m.lda = round_up(std::max<int64_t>(nl, 1), 16);
-  m.A.alloc((size_t)m.lda * n);
+  // same shape as the resident matrix (the cached handle of the drop-in calls, an SCF loop): keep the device block
+  // and its TMA plan, only the contents and the diagonal change
+  const bool reuse = m.kind == DENSE && m.n == n_ && n == n_ && m.A.p != nullptr;
+  if (!reuse) {
+    clear_matrix(which);
+    set_dims(n_);
+    m.lda = round_up(std::max<int64_t>(nl, 1), 16);
+    m.A.alloc((size_t)m.lda * n);
+  }
+  m.diag_valid = false;
   if (nl > 0) h2d_block(m.A.p, m.lda, host + row0, ld, nl, n, stream);
   CK(cudaStreamSynchronize(stream));
   m.kind = DENSE;
@@ -666,9 +672,8 @@ bool dav_solver::orthonormalize_block_pip(int b, int kold) {
     tn_reduce(b, b, T.p, T.p, gemm_ws2, dav::ReduceOut{0, G.p + kold, kb, 0});
   }
   small_ops(1);
-  // The flags of both passes are read while the GPU already runs the final update (and whatever the caller enqueues
-  // next): the update is only WRONG, never harmful, when the flags say so -- the caller then restores the block from
-  // C and takes the fallback path.
+  // The flags of both passes are read while the GPU already runs the final update: the update is only WRONG, never
+  // harmful, when the flags say so -- the caller then restores the block from C and takes the fallback path.
   CK(cudaMemcpyAsync(pip_flags_host, small.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, stream));
   CK(cudaEventRecord(pip_flags_ev, stream));
   // C2 = C1 * Tm - V * (H Tm) = [V | C1] M -> V(:, kold:)
@@ -864,24 +869,21 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
                   (long long)n);
       if (method == DAV_METHOD_GJD) gjd_correction(k, gev, tolerance);  // C <- GJD corrections
       double* Q = V.p + (size_t)k * ldv;
-      const bool pip = orthonormalize_block_pip(k, k);                // steps 6-7 (:210-213), enqueued; reads C
-      if (!pip) {
-        copy_matrix(stream, nl, k, C.p, ldv, Q, ldv);
-        orthonormalize_block(Q, k, k, Q);
-      }
-      auto expand = [&]() {
-        apply_both(Q, k, AV.p + (size_t)k * ldv, gev ? BV.p + (size_t)k * ldv : nullptr);  // the block matvec(s)
-        for (int w = 0; w < (gev ? 2 : 1); ++w) project_new_block(w, k, k);
-      };
-      expand();
-      // the flags of the fast orthonormalisation arrive while the matvec runs; in the rare case that they reject it
-      // (rank-deficient or ill-conditioned block) the block is rebuilt from the corrections, which are still in C
+      // steps 6-7 (:210-213).  The fast path is enqueued up to its last update; its flags arrive while that update
+      // runs, so the host decides without draining the stream.  (A first r02 version also enqueued the block matvec
+      // before looking at the flags: a rejected block -- frequent with the on-the-fly benchmark operator, whose DPR
+      // corrections are nearly parallel -- then costs a whole extra matvec: configs[4] 8.2 -> 16.1 s on 8 GPUs.)
+      bool pip = orthonormalize_block_pip(k, k);
       if (pip && !pip_confirm()) {
         stats.pip_fallbacks += 1;
+        pip = false;
+      }
+      if (!pip) {  // rank-deficient / ill-conditioned block: rebuilt from the corrections, which are still in C
         copy_matrix(stream, nl, k, C.p, ldv, Q, ldv);
         orthonormalize_block(Q, k, k, Q);
-        expand();
       }
+      apply_both(Q, k, AV.p + (size_t)k * ldv, gev ? BV.p + (size_t)k * ldv : nullptr);  // the block matvec(s)
+      for (int w = 0; w < (gev ? 2 : 1); ++w) project_new_block(w, k, k);
       k *= 2;
     } else {                                                          // collapse (:218)
       sp = begin_span(SPAN_ORTH);

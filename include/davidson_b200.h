@@ -82,6 +82,10 @@ int dav_generalized_eigensolver_dense(int64_t n, const double* matrix, int64_t l
                                       int64_t ldb, int lowest, const char* method, int max_iterations,
                                       double tolerance, int max_dim_sub, double* eigenvalues, double* eigenvectors,
                                       int64_t ldv, int* iters);
+/* dav_generalized_eigensolver_dense keeps ONE handle per process between calls (device block of the matrix, TMA plan,
+ * workspace, page-locked staging): a second call with a matrix of the same size only uploads and solves.  This frees
+ * it (the next call allocates again).  Environment DAV_DROPIN_CACHE=0: one handle per call, nothing kept. */
+int dav_release_cache(void);
 
 /* Host callback of the matrix-free path: Y(n x b) = Op * X(n x b), both column-major with leading
  * dimension n (the shape of `fun_matrix_gemv`, davidson.f90:317-325). */

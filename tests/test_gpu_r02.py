@@ -183,8 +183,9 @@ def test_fused_pip_flags_a_dependent_block():
 
 
 def test_rejected_fast_orthonormalisation_is_rebuilt_from_the_corrections():
-    """DAV_PIP_FORCE_REJECT=1: every fast pass is judged as failed after the matvec has already been enqueued on its
-    output; the block must be rebuilt from the corrections by the SVQB loop with the same results."""
+    """DAV_PIP_FORCE_REJECT=1: every fast pass is judged as failed after its last update has already been enqueued
+    (and has overwritten the block); the block must be rebuilt from the corrections by the SVQB loop with the same
+    results."""
     n, L = 3000, 10
     A = orc.generate_diagonal_dominant(n, 5e-2, None, 0)
     r = orc.generalized_eigensolver(A, L, "DPR", 1000, 1e-8, 100)
@@ -362,3 +363,28 @@ def test_device_functor_operator_matches_the_dense_solve(give_diag):
     assert np.abs(ev - es).max() / np.abs(es).max() < EV_RTOL
     for j in range(L):
         assert np.linalg.norm(A @ vec[:, j] - ev[j] * (B @ vec[:, j])) < 1e-8
+
+
+# ---------------------------------------------------------------- cached handle of the drop-in call
+def test_dropin_calls_reuse_the_handle_without_mixing_problems():
+    """dav_generalized_eigensolver_dense keeps one handle per process (device block, TMA plan, workspace): repeated
+    calls must see the NEW matrix (same size), forget a second_matrix that is no longer passed, survive a size
+    change, and dav_release_cache() must leave a working library."""
+    n, L = 900, 3
+    A1 = orc.generate_diagonal_dominant(n, 1e-2, None, 1)
+    A2 = orc.generate_diagonal_dominant(n, 1e-2, None, 2) + 5.0 * np.eye(n)
+    B = orc.generate_diagonal_dominant(n, 1e-3, 1.0, 3)
+    e1, v1, i1 = fd.generalized_eigensolver(A1, L, "DPR", 200, 1e-9)
+    e2, v2, i2 = fd.generalized_eigensolver(A2, L, "DPR", 200, 1e-9)
+    eg, vg, ig = fd.generalized_eigensolver(A1, L, "DPR", 200, 1e-9, None, B)
+    e1b, v1b, i1b = fd.generalized_eigensolver(A1, L, "DPR", 200, 1e-9)          # no second_matrix any more
+    assert np.abs(e1 - sl.eigh(A1, eigvals_only=True)[:L]).max() < 1e-9
+    assert np.abs(e2 - sl.eigh(A2, eigvals_only=True)[:L]).max() < 1e-9
+    assert np.abs(eg - sl.eigh(A1, b=B, eigvals_only=True)[:L]).max() < 1e-9
+    assert np.array_equal(e1, e1b) and np.array_equal(v1, v1b) and i1 == i1b
+    As = orc.generate_diagonal_dominant(300, 1e-2, None, 4)                        # another size
+    es, _, _ = fd.generalized_eigensolver(As, L, "DPR", 200, 1e-9)
+    assert np.abs(es - sl.eigh(As, eigvals_only=True)[:L]).max() < 1e-9
+    check(lib().dav_release_cache())
+    e1c, _, _ = fd.generalized_eigensolver(A1, L, "DPR", 200, 1e-9)
+    assert np.array_equal(e1, e1c)
