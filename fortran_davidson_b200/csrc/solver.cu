@@ -173,12 +173,18 @@ void dav_solver::upload(int which, int64_t n_, const double* host, int64_t ld) {
 
 void dav_solver::upload_rows(int which, int64_t n_, const double* host_rows, int64_t ld) {
   CK(cudaSetDevice(device));
-  clear_matrix(which);
-  set_dims(n_);
-  if (!host_rows || ld < nl) DAV_THROW(DAV_ERR_INVALID, "upload_rows: bad host row block / leading dimension");
   Matrix& m = mat[which];
-  m.lda = round_up(std::max<int64_t>(nl, 1), 16);
-  m.A.alloc((size_t)m.lda * n);
+  const bool reuse = m.kind == DENSE && m.n == n_ && n == n_ && m.A.p != nullptr;  // same shape: keep block + plan
+  if (!reuse) {
+    clear_matrix(which);
+    set_dims(n_);
+  }
+  if (!host_rows || ld < nl) DAV_THROW(DAV_ERR_INVALID, "upload_rows: bad host row block / leading dimension");
+  if (!reuse) {
+    m.lda = round_up(std::max<int64_t>(nl, 1), 16);
+    m.A.alloc((size_t)m.lda * n);
+  }
+  m.diag_valid = false;
   if (nl > 0) h2d_block(m.A.p, m.lda, host_rows, ld, nl, n, stream);
   CK(cudaStreamSynchronize(stream));
   m.kind = DENSE;
