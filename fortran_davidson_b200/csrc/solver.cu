@@ -835,7 +835,10 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
       // eigenvalues = theta(1:L), eigenvectors = V*Y(:, 1:L) of this Rayleigh-Ritz step (:186-187)
       const int spo = begin_span(SPAN_OUT);
       gemm(stream, false, nl, L, k, 1.0, V.p, ldv, Y.p, k, 0.0, T.p, ldv, nullptr, 0);
-      CK(cudaMemcpyAsync(eigenvalues, theta.p, (size_t)L * 8, cudaMemcpyDeviceToHost, stream));
+      // (through the page-locked block: a copy into the caller's pageable array would block the host until the GEMM
+      // above has finished and only then let it enqueue the eigenvector copy)
+      double* ev_host = L <= CONV_HOST_MAX ? pip_flags_host + 16 : eigenvalues;
+      CK(cudaMemcpyAsync(ev_host, theta.p, (size_t)L * 8, cudaMemcpyDeviceToHost, stream));
       int64_t out_rows = 0;
       double* stage = nullptr;
       if (eigenvectors) {
@@ -858,6 +861,7 @@ int dav_solver::solve(int lowest, int method, int max_iterations, double toleran
       }
       end_span(spo);
       CK(cudaStreamSynchronize(stream));
+      if (ev_host != eigenvalues) std::memcpy(eigenvalues, ev_host, (size_t)L * 8);
       if (stage) copy_out(stage, out_rows, L, eigenvectors, ldvec);
       if (converged) break;
     }
