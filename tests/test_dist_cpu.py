@@ -91,3 +91,14 @@ def test_sharded_exchange_pattern_gloo(n):
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(0, "ok"), (1, "ok")], results
+
+
+def test_bind_cpu_to_gpu_is_best_effort():
+    """No NVML / no GPU here: the NUMA binding helper of the multi-rank upload must simply do nothing."""
+    import os
+
+    from fortran_davidson_b200.dist import bind_cpu_to_gpu
+    before = os.sched_getaffinity(0)
+    r = bind_cpu_to_gpu(0)
+    assert r is None or set(r) <= set(before)
+    assert os.sched_getaffinity(0) == before or r is not None

@@ -388,3 +388,22 @@ def test_dropin_calls_reuse_the_handle_without_mixing_problems():
     check(lib().dav_release_cache())
     e1c, _, _ = fd.generalized_eigensolver(A1, L, "DPR", 200, 1e-9)
     assert np.array_equal(e1, e1c)
+
+
+def test_per_phase_spans_are_opt_in():
+    """dav_set_profiling: by default only solve_ms is timed (the ~80 event records of the phase spans cost ~0.1 ms per
+    solve); switched on, the phase times add up to (almost) the total."""
+    s = fd.DavidsonSolver()
+    s.generate_diagonal_dominant(0, 4000, 1e-3, None, 1)
+    s.solve(6, "DPR", 100, 1e-9)
+    st = s.stats()
+    assert st.solve_ms > 0 and st.matvec_ms == 0 and st.rr_ms == 0 and st.kernel_launches > 0
+    s.set_profiling(True)
+    s.solve(6, "DPR", 100, 1e-9)
+    st = s.stats()
+    parts = st.matvec_ms + st.rr_ms + st.orth_ms + st.resid_ms + st.proj_ms + st.init_ms + st.output_ms
+    assert st.matvec_ms > 0 and st.rr_ms > 0 and 0.5 * st.solve_ms < parts <= 1.05 * st.solve_ms
+    s.set_profiling(False)
+    s.solve(6, "DPR", 100, 1e-9)
+    assert s.stats().rr_ms == 0
+    s.close()
