@@ -26,7 +26,6 @@ namespace dav {
 namespace {
 
 constexpr double EPS = 2.220446049250313e-16;
-constexpr double SAFMIN = 2.2250738585072014e-308;
 
 // ---- 1. Householder tridiagonalisation (DSYTD2 on the full symmetric matrix) ----------------------------------
 // Vh(:, j) = reflector j with absolute row indexing (rows <= j are 0, row j+1 is 1); tau[j] = 0 for H_j = I.
