@@ -680,13 +680,19 @@ def run_e2e(args, solver, fd, torch, dist, distributed, rank, world, n, L, md, b
         if i > 0:
             times.append(time.perf_counter() - t0)
     t = max_over_ranks(sum(times) / len(times))
+    moved = C.c_double(0.0)
+    fd._lib.check(fd.lib().dav_upload_bytes(None if world == 1 else solver._h, C.byref(moved)))
+    h2d_bytes = int(moved.value) if world == 1 else int(8 * nl * n * world)
     if world == 1:
         fd._lib.check(fd.lib().dav_release_cache())  # the drop-in call keeps its handle (80 GB) between calls
     else:
         solver.clear(0)
     if pinned:
         rt.cudaHostUnregister(ptr)
-    return {"value": t, "unit": UNIT, "h2d_bytes_per_step": int(8 * nl * n * world),
+    return {"value": t, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+            "host_matrix_bytes": int(8 * nl * n * world),
+            "upload": ("upper triangle only (the host matrix passed the library's sampled symmetry check), mirrored on "
+                       "the device" if world == 1 and h2d_bytes < 0.75 * 8 * nl * n else "full row block(s)"),
             "d2h_bytes_per_step": int(8 * n * L + 8 * L), "steps": steps,
             "api": "dav_generalized_eigensolver_dense (host pointers, pinned; the library's cached handle is warm after "
                    "the untimed first call: no cudaMalloc of the matrix inside the timed calls)" if world == 1 else

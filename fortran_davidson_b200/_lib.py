@@ -17,7 +17,7 @@ DEVICE_GEMV_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
 
 # every symbol include/davidson_b200.h declares
 SYMBOLS = [
-    "dav_last_error", "dav_version", "dav_device_count", "dav_set_default_device", "dav_generalized_eigensolver_dense", "dav_release_cache",
+    "dav_last_error", "dav_version", "dav_device_count", "dav_set_default_device", "dav_generalized_eigensolver_dense", "dav_release_cache", "dav_upload_bytes",
     "dav_generalized_eigensolver_free", "dav_generalized_eigensolver_free_builtin", "dav_get_unique_id",
     "dav_create", "dav_create_distributed", "dav_destroy", "dav_alloc_pinned", "dav_free_pinned", "dav_partition_rows",
     "dav_matrix_generate_diagonal_dominant", "dav_matrix_upload", "dav_matrix_upload_rows",

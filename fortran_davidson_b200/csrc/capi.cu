@@ -570,6 +570,15 @@ int dav_generalized_eigensolver_dense(int64_t n, const double* matrix, int64_t l
   API_END
 }
 
+int dav_upload_bytes(dav_solver_t* h, double* bytes) {
+  API_BEGIN
+  need(bytes != nullptr, "bad arguments");
+  std::unique_lock<std::mutex> lock(g_dropin_mu);
+  const dav_solver* s = h ? h : g_dropin;
+  *bytes = s ? s->last_upload_bytes : 0.0;
+  API_END
+}
+
 int dav_release_cache(void) {
   API_BEGIN
   std::unique_lock<std::mutex> lock(g_dropin_mu);

@@ -68,6 +68,8 @@ struct dav_solver {
   void generate_diagonal_dominant(int which, int64_t n, double sparsity, int has_diag, double diag_val,
                                   uint64_t seed);
   void upload(int which, int64_t n, const double* host, int64_t ld);
+  bool host_looks_symmetric(const double* host, int64_t ld, int64_t n);
+  double last_upload_bytes = 0;  // bytes the last upload moved over PCIe (the symmetric upload moves half)
   void upload_rows(int which, int64_t n, const double* host_rows, int64_t ld);
   void set_operator(int which, int64_t n, int op);
   void set_callback(int which, int64_t n, dav_gemv_fn fn, void* ctx, const double* diag);

@@ -142,6 +142,24 @@ __global__ void __launch_bounds__(TOPK_CHUNK) rank_select_kernel(const double* _
   (void)final_round;
 }
 
+// lower triangle <- upper triangle of the n x n matrix A (lda), 32 x 32 tiles through shared memory; block (ti, tj)
+// with ti >= tj writes tile (rows of ti, columns of tj) from the transposed upper tile (rows of tj, columns of ti)
+__global__ void __launch_bounds__(256) mirror_upper_kernel(double* __restrict__ A, int64_t lda, int64_t n) {
+  const int64_t ti = blockIdx.y, tj = blockIdx.x;
+  if (tj > ti) return;
+  __shared__ double tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int q = ty; q < 32; q += 8) {  // upper tile: rows tj*32 + tx, columns ti*32 + q
+    const int64_t r = tj * 32 + tx, c = ti * 32 + q;
+    tile[q][tx] = (r < n && c < n) ? A[r + c * lda] : 0.0;
+  }
+  __syncthreads();
+  for (int q = ty; q < 32; q += 8) {  // lower tile: rows ti*32 + tx, columns tj*32 + q  <-  upper (tj*32 + q, ti*32 + tx)
+    const int64_t r = ti * 32 + tx, c = tj * 32 + q;
+    if (r < n && c < n && r > c) A[r + c * lda] = tile[tx][q];
+  }
+}
+
 // X (n x w) = columns c0 .. c0 + w of the identity
 __global__ void unit_block_kernel(double* __restrict__ X, int64_t n, int64_t c0, int w) {
   const int64_t total = n * w;
@@ -344,6 +362,13 @@ void topk_smallest(cudaStream_t s, const double* diag, const int64_t* gidx, int6
     cv = ov; ci = oi; m = nch * k; r0 = 0;
     side ^= 1;
   }
+}
+
+void mirror_upper_to_lower(cudaStream_t s, double* A, int64_t lda, int64_t n) {
+  if (n <= 1) return;
+  const unsigned nt = (unsigned)((n + 31) / 32);
+  mirror_upper_kernel<<<dim3(nt, nt), 256, 0, s>>>(A, lda, n);
+  LAUNCHED();
 }
 
 void unit_block(cudaStream_t s, double* X, int64_t n, int64_t c0, int w) {

@@ -199,6 +199,11 @@ int dav_get_stats(dav_solver_t* h, dav_stats_t* out);
  * comm_ms of dav_stats_t; ~80 event records per solve, ~0.1 ms).  Default 0: only solve_ms is timed, the per-phase
  * fields stay 0.  The environment variable DAV_SPANS=1 switches the spans on for every handle. */
 int dav_set_profiling(dav_solver_t* h, int per_phase_spans);
+/* Bytes the last matrix upload of handle h moved over PCIe (h == NULL: the cached handle of the drop-in call).  On one
+ * GPU a host matrix that passes a sampled symmetry check (2^17 random pairs compared exactly) is uploaded as its
+ * upper triangle only and mirrored on the device -- DSYEV 'U' semantics, half the bytes; an input that fails the
+ * check, several ranks, n < 2048 or DAV_SYMMETRIC_UPLOAD=0 take the full upload. */
+int dav_upload_bytes(dav_solver_t* h, double* bytes);
 
 /* knobs: DAV_MATVEC_* implementation of the block matvec */
 int dav_set_matvec_impl(dav_solver_t* h, int impl);

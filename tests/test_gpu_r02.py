@@ -407,3 +407,31 @@ def test_per_phase_spans_are_opt_in():
     s.solve(6, "DPR", 100, 1e-9)
     assert s.stats().rr_ms == 0
     s.close()
+
+
+def test_symmetric_upload_moves_one_triangle_and_is_exact():
+    """One GPU, symmetric host matrix: only the upper triangle crosses PCIe, the device mirrors it -- the resident matrix
+    must be bit-identical to the host matrix; an asymmetric host matrix must take the full upload unchanged."""
+    n = 3000
+    A = orc.generate_diagonal_dominant(n, 1e-3, None, 9)
+    s = fd.DavidsonSolver()
+    s.upload(0, A)
+    moved = C.c_double(0.0)
+    check(lib().dav_upload_bytes(s._h, C.byref(moved)))
+    assert 0.5 * 8 * n * n <= moved.value <= 0.52 * 8 * n * n
+    assert np.array_equal(s.download(0), A)
+    # padded leading dimension on the host side
+    blk = np.zeros((n + 7, n), order="F")
+    blk[:n] = A
+    s.upload_ptr(0, n, blk.ctypes.data, n + 7)
+    assert np.array_equal(s.download(0), A)
+    # not symmetric: everything is uploaded as given
+    N = A.copy()
+    N[np.tril_indices(n, -1)] += 1.0
+    s.upload(0, N)
+    check(lib().dav_upload_bytes(s._h, C.byref(moved)))
+    assert moved.value == 8.0 * n * n
+    assert np.array_equal(s.download(0), N)
+    ev, vec, it = fd.generalized_eigensolver(A, 4, "DPR", 200, 1e-9)
+    assert np.abs(ev - sl.eigh(A, eigvals_only=True)[:4]).max() < 1e-9
+    s.close()
