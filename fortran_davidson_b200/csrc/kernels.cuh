@@ -153,7 +153,9 @@ void topk_smallest(cudaStream_t s, const double* diag, const int64_t* gidx /*nul
                    int64_t row0, int k, double* out_val, int64_t* out_idx, int* status, double* scratch_val,
                    int64_t* scratch_idx);
 // A(i, j) <- A(j, i) for i > j (n x n, lda): completes a matrix of which only the upper triangle was uploaded
-void mirror_upper_to_lower(cudaStream_t s, double* A, int64_t lda, int64_t n);
+// (rows [row_begin, row_end) of the lower triangle only when given: multiples of 32, row_end < 0 = n)
+void mirror_upper_to_lower(cudaStream_t s, double* A, int64_t lda, int64_t n, int64_t row_begin = 0,
+                           int64_t row_end = -1);
 // X (n x w, ld n) = columns c0 .. c0 + w of the identity; diag[i - row0] = Y(i - row0, i - c0) for the owned rows of
 // that column range (extract_diagonal_free, davidson.f90:490-523, with the block on the device)
 void unit_block(cudaStream_t s, double* X, int64_t n, int64_t c0, int w);

@@ -70,6 +70,7 @@ dav_solver::~dav_solver() {
   if (pip_flags_ev) cudaEventDestroy(pip_flags_ev);
   if (pip_flags_host) cudaFreeHost(pip_flags_host);
   if (pinned_out) cudaFreeHost(pinned_out);
+  if (stream2) cudaStreamDestroy(stream2);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -172,14 +173,29 @@ void dav_solver::upload(int which, int64_t n_, const double* host, int64_t ld) {
   // pairs, exact comparison); anything else takes the full upload.  DAV_SYMMETRIC_UPLOAD=0 switches it off.
   static const bool sym_enabled = [] { const char* e = std::getenv("DAV_SYMMETRIC_UPLOAD"); return !(e && std::atoi(e) == 0); }();
   if (sym_enabled && comm.world() == 1 && n >= 2048 && nl == n && host_looks_symmetric(host, ld, n)) {
-    const int64_t w = round_up(ceil_div(n, 128), 16);  // column panels: rows 0 .. panel end
+    const int64_t w = round_up(ceil_div(n, 128), 32);  // column panels (whole 32 x 32 tiles): rows 0 .. panel end
+    // panel p is mirrored on a second stream while panel p+1 is still crossing PCIe
+    if (!stream2) CK(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
+    std::vector<cudaEvent_t> evs;
     for (int64_t c0 = 0; c0 < n; c0 += w) {
       const int64_t c1 = std::min(n, c0 + w);
       CK(cudaMemcpy2DAsync(m.A.p + (size_t)c0 * m.lda, (size_t)m.lda * 8, host + (size_t)c0 * ld, (size_t)ld * 8,
                            (size_t)c1 * 8, (size_t)(c1 - c0), cudaMemcpyHostToDevice, stream));
       last_upload_bytes += (double)c1 * 8.0 * (double)(c1 - c0);
+      cudaEvent_t e;
+      CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      evs.push_back(e);
+      CK(cudaEventRecord(e, stream));
+      CK(cudaStreamWaitEvent(stream2, e, 0));
+      mirror_upper_to_lower(stream2, m.A.p, m.lda, n, c0, c1);  // rows c0 .. c1 of the lower triangle
     }
-    mirror_upper_to_lower(stream, m.A.p, m.lda, n);
+    cudaEvent_t done;
+    CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    evs.push_back(done);
+    CK(cudaEventRecord(done, stream2));
+    CK(cudaStreamWaitEvent(stream, done, 0));
+    CK(cudaStreamSynchronize(stream));
+    for (cudaEvent_t e : evs) cudaEventDestroy(e);
   } else if (nl > 0) {
     h2d_block(m.A.p, m.lda, host + row0, ld, nl, n, stream);
     last_upload_bytes = 8.0 * (double)nl * (double)n;

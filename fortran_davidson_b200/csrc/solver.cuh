@@ -25,6 +25,7 @@ struct dav_solver {
 
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // mirrors the uploaded panels of a symmetric matrix while the next ones arrive
   dav::Comm comm;
   int64_t n = 0, nl = 0, row0 = 0, chunk = 0;  // global size, local rows, first local row, rows per rank
   Matrix mat[2];

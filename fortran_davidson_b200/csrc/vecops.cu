@@ -144,8 +144,9 @@ __global__ void __launch_bounds__(TOPK_CHUNK) rank_select_kernel(const double* _
 
 // lower triangle <- upper triangle of the n x n matrix A (lda), 32 x 32 tiles through shared memory; block (ti, tj)
 // with ti >= tj writes tile (rows of ti, columns of tj) from the transposed upper tile (rows of tj, columns of ti)
-__global__ void __launch_bounds__(256) mirror_upper_kernel(double* __restrict__ A, int64_t lda, int64_t n) {
-  const int64_t ti = blockIdx.y, tj = blockIdx.x;
+__global__ void __launch_bounds__(256) mirror_upper_kernel(double* __restrict__ A, int64_t lda, int64_t n,
+                                                           int64_t tile_row0) {
+  const int64_t ti = tile_row0 + blockIdx.y, tj = blockIdx.x;
   if (tj > ti) return;
   __shared__ double tile[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -364,10 +365,13 @@ void topk_smallest(cudaStream_t s, const double* diag, const int64_t* gidx, int6
   }
 }
 
-void mirror_upper_to_lower(cudaStream_t s, double* A, int64_t lda, int64_t n) {
-  if (n <= 1) return;
-  const unsigned nt = (unsigned)((n + 31) / 32);
-  mirror_upper_kernel<<<dim3(nt, nt), 256, 0, s>>>(A, lda, n);
+void mirror_upper_to_lower(cudaStream_t s, double* A, int64_t lda, int64_t n, int64_t row_begin, int64_t row_end) {
+  // rows [row_begin, row_end) of the lower triangle (both multiples of 32, or row_end == n) from columns of the same
+  // range of the upper triangle: lets the caller mirror a column panel as soon as it has arrived
+  if (row_end < 0) row_end = n;
+  if (n <= 1 || row_end <= row_begin) return;
+  const unsigned t0 = (unsigned)(row_begin / 32), t1 = (unsigned)((row_end + 31) / 32);
+  mirror_upper_kernel<<<dim3(t1, t1 - t0), 256, 0, s>>>(A, lda, n, (int64_t)t0);
   LAUNCHED();
 }
 
