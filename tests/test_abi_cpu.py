@@ -140,3 +140,19 @@ def test_example_programs_compile():
             if isinstance(node, (ast.Import, ast.ImportFrom)):
                 mod = node.module if isinstance(node, ast.ImportFrom) else node.names[0].name
                 assert not (mod or "").startswith("oracle"), f
+
+
+def test_every_environment_switch_is_documented():
+    """Every DAV_* environment variable the library reads is listed in README.md (the switch list a maintainer of the
+    reference would look at); compile-time macros and enum names are not switches."""
+    import re
+    src = os.path.join(ROOT, "fortran_davidson_b200", "csrc")
+    read = set()
+    for f in os.listdir(src):
+        if f.endswith((".cu", ".cuh", ".h", ".cpp")):
+            text = open(os.path.join(src, f)).read()
+            read |= set(re.findall(r'(?:getenv|env_int|env_flag)\(\s*"(DAV_[A-Z0-9_]+)"', text))
+    assert len(read) >= 15, read
+    readme = open(os.path.join(ROOT, "README.md")).read()
+    missing = sorted(v for v in read if v not in readme)
+    assert not missing, missing
