@@ -323,3 +323,122 @@ def test_stats_struct_mirrors_the_header():
     assert [w[0] for w in want] == [g[0] for g in got]
     for (name, base, n), (_, t) in zip(want, got):
         assert t is (ctype[base] * n if n else ctype[base]) or (n and t._type_ is ctype[base] and t._length_ == n), (name, t)
+
+
+def _fortran_logical_lines(path):
+    """Free-form source -> statements: comments stripped (outside strings), `&` continuations joined, lower-cased
+    outside strings.  Returns [(first line number, statement)]."""
+    out, cur, start = [], "", 0
+    for no, raw in enumerate(open(path), 1):
+        line, quote, i = "", None, 0
+        while i < len(raw.rstrip("\n")):
+            ch = raw[i]
+            if quote:
+                line += ch
+                if ch == quote:
+                    quote = None
+            elif ch in "'\"":
+                quote = ch
+                line += ch
+            elif ch == "!":
+                break
+            else:
+                line += ch.lower()
+            i += 1
+        line = line.strip()
+        if not line:
+            continue
+        if cur and line.startswith("&"):
+            line = line[1:].lstrip()
+        if not cur:
+            start = no
+        if line.endswith("&"):
+            cur += line[:-1]
+            continue
+        out.append((start, cur + line))
+        cur = ""
+    assert not cur
+    return out
+
+
+def _split_top_level(args):
+    parts, depth, quote, cur = [], 0, None, ""
+    for ch in args:
+        if quote:
+            cur += ch
+            if ch == quote:
+                quote = None
+            continue
+        if ch in "'\"":
+            quote = ch
+        elif ch in "([":
+            depth += 1
+        elif ch in ")]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            parts.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        parts.append(cur.strip())
+    return parts
+
+
+def test_fortran_shim_blocks_balance_and_c_calls_pass_the_declared_argument_count(capfd):
+    """Two checks a compiler would make and a declaration parser does not: every block construct of the shim closes
+    with its own `end` (module / subroutine / function / interface / do / if-then / select), and every reference to a
+    `dav_*` C entry point passes exactly as many actual arguments as its bind(C) interface declares."""
+    import re
+    path = os.path.join(ROOT, "fortran", "davidson.f90")
+    stmts = _fortran_logical_lines(path)
+    stack = []
+    openers = [
+        ("module", r"module\s+(?!procedure\b)\w+$"), ("program", r"program\s+\w+$"),
+        ("interface", r"(abstract\s+)?interface(\s+\w+)?$"),
+        ("subroutine", r"((pure|elemental|recursive|module)\s+)*subroutine\s+\w+"),
+        ("function", r"((pure|elemental|recursive|module|real\s*\(\w+\)|integer|logical)\s+)*function\s+\w+"),
+        ("do", r"(\w+\s*:\s*)?do(\s|$)"), ("if", r"(\w+\s*:\s*)?if\s*\(.*\)\s*then$"),
+        ("select", r"select\s+(case|type)\b"), ("type", r"type\s*(,[^:]*)?(::)?\s*\w+$"),
+    ]
+    for no, st in stmts:
+        m = re.match(r"end\s*(module|program|interface|subroutine|function|do|if|select|type)\b", st)
+        if m:
+            assert stack and stack[-1][0] == m.group(1), (no, st, stack[-3:])
+            stack.pop()
+            continue
+        assert not re.match(r"end\s*$", st), (no, "bare `end`: name the construct")
+        for kind, pat in openers:
+            if re.match(pat, st) and not (kind == "type" and "(" in st.split("::")[0]):
+                stack.append((kind, no))
+                break
+    assert not stack, stack
+
+    tool = _load_interface_tool()
+    tree = tool.crack([path])
+    capfd.readouterr()
+    nargs = {}
+
+    def walk(b):
+        if b.get("block") in ("function", "subroutine") and b["name"].startswith("dav_"):
+            nargs[b["name"]] = len(b["args"])
+        for c in b.get("body", []):
+            walk(c)
+    for b in tree:
+        walk(b)
+    calls = 0
+    for no, st in stmts:
+        if re.match(r"(end\s+)?(function|subroutine)\b", st) or "bind(c" in st.replace(" ", ""):
+            continue  # the declarations themselves
+        for m in re.finditer(r"\b(dav_\w+)\s*\(", st):
+            name = m.group(1)
+            if name not in nargs:
+                continue
+            depth, j = 1, m.end()
+            while depth:
+                depth += {"(": 1, ")": -1}.get(st[j], 0)
+                j += 1
+            actual = _split_top_level(st[m.end():j - 1])
+            assert len(actual) == nargs[name], (no, name, len(actual), nargs[name])
+            calls += 1
+    assert calls >= 13, calls
