@@ -2,8 +2,9 @@
 
 The CUDA driver (fortran_davidson_b200/csrc/solver.cu) does not run the reference's statements
 literally: it keeps V / AV / BV resident and incremental, takes residuals from the stored
-products, orthonormalises only the new block (project out V twice + SVQB), and solves the
-projected problems with a parallel-ordering two-sided Jacobi.  This file restates exactly that
+products, orthonormalises only the new block (r02: two passes of BCGS-PIP, `bcgs_pip2`; r01 and the
+fallback: project out V twice + SVQB), and solves the projected problems with a parallel-ordering
+two-sided Jacobi (r02 default for k >= 16: tridiagonalisation + bisection, same eigenpairs).  This file restates exactly that
 flow in numpy so that the CPU suite can check, without a GPU, that the flow is
 subspace-equivalent to the reference (same iteration count, same eigenvalues) -- see
 tests/test_device_model.py.  The kernels' arithmetic is mirrored step by step; names follow
@@ -100,8 +101,65 @@ def svqb(C, V, passes=2):
     return C
 
 
+def pip_small(H, Gc, mode):
+    """csrc/smalldense.cu pip_small_kernel: H = V^T C (kold x b), Gc = C^T C -> M = [-H Tm; Tm] with
+    Tm^T (Gc - H^T H) Tm = I, and the four metrics the host judges (m0, m1, diagonal unsafe, pivot unsafe)."""
+    b = Gc.shape[0]
+    Gp = Gc - H.T @ H
+    d, cc = np.diag(Gp).copy(), np.diag(Gc).copy()
+    badd = bool(np.any(~(cc > 0.0) | ~(d > 1e-10 * cc)))
+    cn = np.where(cc > 0, 1.0 / np.sqrt(np.where(cc > 0, cc, 1.0)), 0.0)
+    m0 = float(np.max(np.abs(H) * cn[None, :])) if H.size else 0.0
+    bad = False
+    if badd:
+        return None, (m0, 0.0, 1.0, 0.0)
+    if mode == 0:  # first pass: scaled Cholesky + inverse
+        D = 1.0 / np.sqrt(d)
+        Gs = Gp * D[:, None] * D[None, :]
+        m1 = float(np.max(np.abs(Gs - np.eye(b))))
+        R = Gs.copy()  # right-looking, upper triangle, pivots checked against the original diagonal
+        d0 = np.diag(Gs).copy()
+        for j in range(b):
+            piv = R[j, j]
+            if not (piv > 1e-12 * abs(d0[j])) or not (d0[j] > 0.0):
+                bad = True
+                break
+            R[j, j:] = R[j, j:] / np.sqrt(piv)
+            for i in range(j + 1, b):
+                R[i, i:] -= R[j, i] * R[j, i:]
+        if bad:
+            return None, (m0, m1, 0.0, 1.0)
+        R = np.triu(R)
+        Tm = D[:, None] * np.linalg.solve(R, np.eye(b))
+        flag = 0.0
+    else:  # second pass: G' = I + E, Tm = (I + E)^-1/2 to second order
+        E = Gp - np.eye(b)
+        m1 = float(np.max(np.abs(E)))
+        Tm = np.eye(b) - 0.5 * E + 0.375 * (E @ E)
+        flag = 0.0 if m1 < 1e-5 else 1.0
+    return np.vstack([-H @ Tm, Tm]), (m0, m1, flag, 0.0)
+
+
+def bcgs_pip2(C, V, stats=None):
+    """csrc/solver.cu orthonormalize_block_pip + pip_confirm: two passes of block classical Gram-Schmidt with the
+    Pythagorean inner product; any raised flag, or a second pass that did not start from a block orthonormal to 1e-6,
+    rejects the result and the block is rebuilt from the corrections by the SVQB loop."""
+    M1, f1 = pip_small(V.T @ C, C.T @ C, 0)
+    ok = M1 is not None
+    if ok:
+        C1 = np.hstack([V, C]) @ M1
+        M2, f2 = pip_small(V.T @ C1, C1.T @ C1, 1)
+        ok = M2 is not None and f1[2] == 0.0 and f1[3] == 0.0 and f2[2] == 0.0 and f2[3] == 0.0 and \
+            f2[0] < 1e-6 and f2[1] < 1e-6
+    if stats is not None:
+        stats["pip_accepted" if ok else "pip_fallbacks"] = stats.get("pip_accepted" if ok else "pip_fallbacks", 0) + 1
+    if not ok:
+        return svqb(C, V)
+    return np.hstack([V, C1]) @ M2
+
+
 def solve_dense(A, lowest, method, max_iterations, tolerance, max_dim_sub=None, B=None, free_semantics=False,
-                diagA=None, diagB=None, apply_A=None, apply_B=None):
+                diagA=None, diagB=None, apply_A=None, apply_B=None, ortho="svqb", stats=None):
     n = A.shape[0] if A is not None else diagA.size
     gev = (B is not None) or (apply_B is not None)
     mulA = (lambda X: A @ X) if apply_A is None else apply_A
@@ -143,7 +201,7 @@ def solve_dense(A, lowest, method, max_iterations, tolerance, max_dim_sub=None, 
                 C = R / (theta[None, :] * dB[:, None] - dA[:, None])
             else:
                 raise NotImplementedError
-            Q = svqb(C, V)
+            Q = svqb(C, V) if ortho == "svqb" else bcgs_pip2(C, V, stats)
             AQ = mulA(Q)
             Vn = np.hstack([V, Q])
             Apn = np.zeros((2 * k, 2 * k)); Apn[:k, :k] = Ap
@@ -255,7 +313,7 @@ def gjd_block_minres(mulA, mulB, theta, U, W, R, dA, dB, rtol=GJD_RTOL, maxit=GJ
     return x, its
 
 
-def solve_dense_gjd(A, lowest, max_iterations, tolerance, max_dim_sub=None, B=None):
+def solve_dense_gjd(A, lowest, max_iterations, tolerance, max_dim_sub=None, B=None, ortho="svqb", stats=None):
     """solve_dense with the GJD correction (dense path only, like the reference)."""
     n = A.shape[0]
     gev = B is not None
@@ -287,7 +345,7 @@ def solve_dense_gjd(A, lowest, max_iterations, tolerance, max_dim_sub=None, B=No
         if k <= max_dim:
             C, nin = gjd_block_minres(lambda X: A @ X, (lambda X: B @ X) if gev else None, theta, U, W, R, dA, dB)
             inner.append(nin)
-            Q = svqb(C, V)
+            Q = svqb(C, V) if ortho == "svqb" else bcgs_pip2(C, V, stats)
             AQ = A @ Q
             Vn = np.hstack([V, Q])
             Apn = np.zeros((2 * k, 2 * k)); Apn[:k, :k] = Ap

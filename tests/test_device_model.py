@@ -71,3 +71,57 @@ def test_model_gjd_harder_cases():
             ev, X, iters, tk, inner = dm.solve_dense_gjd(A, L, 100, tol, md, Bm)
             assert abs(iters - r.iters) <= 1
             assert np.abs(ev - r.eigenvalues).max() / np.abs(ev).max() < 1e-10
+
+
+@pytest.mark.parametrize("name", ["matrix_txt_DPR", "readme_std_DPR", "readme_gev_DPR", "test_dense_numpy_gen_DPR",
+                                  "main_f90_DPR", "collapse_n1000_DPR", "collapse_n1000_gev_DPR"])
+def test_model_with_bcgs_pip2_parity_with_oracle(name, golden_cases):
+    """r02 block orthonormalisation (two passes of BCGS with the Pythagorean inner product, scaled Cholesky in the
+    first pass, (I + E)^-1/2 series in the second, SVQB only when a flag rejects the pass): the expansion spans the
+    same subspace as the reference's Householder QR of [V | correction] (davidson.f90:205-209), so iteration count,
+    basis schedule, eigenvalues and eigenvectors are the oracle's."""
+    g = golden_cases[name]
+    A, B = case_inputs(name)
+    stats = {}
+    ev, X, iters, tk, te = dm.solve_dense(A, g["lowest"], "DPR", g["max_iterations"], g["tolerance"],
+                                          g["max_dim_sub"], B, ortho="pip", stats=stats)
+    assert iters == g["iters"] and list(tk) == g["trace_k"]
+    assert np.abs(ev - np.array(g["eigenvalues"])).max() / np.abs(ev).max() < 1e-10
+    r = orc.generalized_eigensolver(A, g["lowest"], "DPR", g["max_iterations"], g["tolerance"], g["max_dim_sub"], B)
+    for j in range(g["lowest"]):
+        s = np.sign(X[:, j] @ r.eigenvectors[:, j])
+        assert np.abs(s * X[:, j] - r.eigenvectors[:, j]).max() < 1e-8
+    # these inputs are well conditioned: the fast path must be the one that ran
+    assert stats.get("pip_accepted", 0) >= 1 and stats.get("pip_fallbacks", 0) == 0, stats
+
+
+def test_bcgs_pip2_block_is_orthonormal_and_spans_the_corrections():
+    rng = np.random.default_rng(5)
+    n, k, b = 400, 24, 12
+    V, _ = np.linalg.qr(rng.standard_normal((n, k)))
+    C = rng.standard_normal((n, b)) * np.logspace(0, 6, b)[None, :]   # badly scaled columns
+    C[:, 3] += 1e3 * V[:, 1]                                          # mostly inside span(V)
+    stats = {}
+    Q = dm.bcgs_pip2(C, V, stats)
+    assert stats == {"pip_accepted": 1}
+    assert np.abs(Q.T @ Q - np.eye(b)).max() < 1e-13 and np.abs(V.T @ Q).max() < 1e-13
+    # same subspace as a Householder QR of [V | C] restricted to the new block
+    Qh = np.linalg.qr(np.hstack([V, C]))[0][:, k:]
+    assert np.abs(Qh @ (Qh.T @ Q) - Q).max() < 1e-9
+
+
+def test_bcgs_pip2_rejects_a_dependent_block_and_falls_back():
+    rng = np.random.default_rng(6)
+    n, k, b = 300, 16, 8
+    V, _ = np.linalg.qr(rng.standard_normal((n, k)))
+    C = rng.standard_normal((n, b))
+    C[:, 5] = C[:, 2]                       # exactly dependent columns: the Cholesky pivot is unsafe
+    stats = {}
+    Q = dm.bcgs_pip2(C, V, stats)
+    assert stats == {"pip_fallbacks": 1}
+    assert np.abs(Q.T @ Q - np.eye(b)).max() < 1e-8 and np.abs(V.T @ Q).max() < 1e-8
+    C2 = rng.standard_normal((n, b))
+    C2[:, 0] = V[:, 3] + 1e-9 * C2[:, 0]    # a correction that lies in span(V) to round-off: diagonal unsafe
+    stats = {}
+    dm.bcgs_pip2(C2, V, stats)
+    assert stats == {"pip_fallbacks": 1}
