@@ -65,16 +65,158 @@ def jacobi_eigh(S_in, max_sweeps=40):
     return w[order], V[:k, :k][:, order]
 
 
-def sygv(Ap, Bp):
+# ------------------------------------------------------------------------------------------------
+# r02 Rayleigh-Ritz eigensolver (csrc/trideig.cu), the default for k >= 16: Householder tridiagonalisation,
+# every eigenpair on its own (bisection on the Sturm count, twisted factorisation, back-transformation),
+# one Newton-Schulz step + Rayleigh quotients as the guard, Jacobi when the guard refuses.
+# ------------------------------------------------------------------------------------------------
+EIGH_TRIDIAG_MIN_K = 16
+
+
+def householder_tridiag(S):
+    """tridiag_reg_kernel: S = Q T Q^T with T = tridiag(e, d, e); reflector j in Vh(:, j) (rows <= j zero, row j+1
+    one), tau[j] = 0 for H_j = I."""
+    k = S.shape[0]
+    S = S.copy()
+    Vh, tau, d, e = np.zeros((k, k)), np.zeros(k), np.zeros(k), np.zeros(max(k - 1, 0))
+    for j in range(k - 2):
+        col = S[j + 1:, j]
+        alpha, sigma = col[0], float((col[1:] ** 2).sum())
+        v = np.zeros(k - j - 1); v[0] = 1.0
+        t, beta = 0.0, alpha
+        if sigma > 0.0:
+            nrm = np.sqrt(alpha * alpha + sigma)
+            beta = -np.copysign(nrm, alpha)
+            t = 1.0 + abs(alpha) / nrm
+            v[1:] = col[1:] * np.copysign(1.0 / (abs(alpha) + nrm), alpha)
+        d[j], e[j] = S[j, j], beta
+        Vh[j + 1:, j], tau[j] = v, t
+        sub = S[j + 1:, j + 1:]
+        pvec = t * (sub @ v)
+        w = pvec - 0.5 * t * (pvec @ v) * v
+        sub -= np.outer(v, w) + np.outer(w, v)
+    if k >= 2:
+        d[k - 2], e[k - 2] = S[k - 2, k - 2], S[k - 1, k - 2]
+    d[k - 1] = S[k - 1, k - 1]
+    return d, e, Vh, tau
+
+
+def sturm_count(ds, e2s, x):
+    """#{eigenvalues < x}: sign changes of p_0 = 1, p_1 = d_0 - x, p_{i+1} = (d_i - x) p_i - e_{i-1}^2 p_{i-1};
+    a zero takes the sign opposite to its predecessor."""
+    pm, pc = 1.0, ds[0] - x
+    neg = not (pc > 0.0)
+    cnt = int(neg)
+    for i in range(1, ds.size):
+        pn = (ds[i] - x) * pc - e2s[i - 1] * pm
+        nneg = (not neg) if pn == 0.0 else (pn < 0.0)
+        cnt += int(nneg != neg)
+        neg = nneg
+        pm, pc = pc, pn
+        mag = max(abs(pc), abs(pm))
+        if mag > 1e100 or mag < 1e-100:
+            f = 1e-100 if mag > 1e100 else 1e100
+            pc *= f; pm *= f
+    return cnt
+
+
+def tri_eigpair(ds, es, j):
+    """tri_eigvec_kernel for eigenvalue j (ascending) of the scaled tridiagonal matrix: interval refinement on the
+    Sturm count until it is 4 eps wide, then the twisted factorisation at r = argmin |gamma_i|."""
+    k = ds.size
+    e2s = es * es
+    r_ = np.zeros(k); r_[:-1] += np.abs(es[:-1]) if k > 1 else 0.0; r_[1:] += np.abs(es[:-1]) if k > 1 else 0.0
+    lo = float((ds - r_).min()) - 4 * EPS * k - 1e-300
+    hi = float((ds + r_).max()) + 4 * EPS * k + 1e-300
+    for _ in range(400):
+        width = hi - lo
+        if not (width > max(4 * EPS * max(abs(lo), abs(hi)), 1e-3 * EPS)):
+            break
+        x = lo + 0.5 * width
+        if sturm_count(ds, e2s, x) >= j + 1:
+            hi = x
+        else:
+            lo = x
+    lam = 0.5 * (lo + hi)
+
+    def pivots(order):
+        q = np.zeros(k)
+        pm, pc = 1.0, ds[order[0]] - lam
+        q[order[0]] = pc
+        for s_ in range(1, k):
+            i_prev, i = order[s_ - 1], order[s_]
+            ee = e2s[min(i_prev, i)]
+            pn = (ds[i] - lam) * pc - ee * pm
+            q[i] = pn / pc if pc != 0.0 else np.inf
+            pm, pc = pc, pn
+            mag = max(abs(pc), abs(pm))
+            if mag > 1e100 or (0 < mag < 1e-100):
+                f = 1e-100 if mag > 1e100 else 1e100
+                pc *= f; pm *= f
+        return q
+    qp, qm = pivots(list(range(k))), pivots(list(range(k - 1, -1, -1)))
+    for q in (qp, qm):
+        small = ~(np.abs(q) >= EPS)
+        q[small] = np.where(q[small] < 0.0, -EPS, EPS)
+    gamma = np.abs(qp + qm - (ds - lam))
+    r = int(np.argmin(gamma))
+    z = np.zeros(k); z[r] = 1.0
+    for i in range(r - 1, -1, -1):
+        z[i] = -es[i] / qp[i] * z[i + 1]
+    for i in range(r + 1, k):
+        z[i] = -es[i - 1] / qm[i] * z[i - 1]
+    return lam, z / np.sqrt(z @ z)
+
+
+def tridiag_eigh(S, stats=None):
+    """sym_eigh for k >= EIGH_TRIDIAG_MIN_K: returns (eigenvalues ascending, eigenvectors).  The guard accepts the
+    independent eigenvector computations only if they are orthonormal to 3e-8 before the Newton-Schulz step and the
+    residuals are at round-off level; otherwise the Jacobi solver runs (exactly degenerate / tightly clustered
+    spectra)."""
+    k = S.shape[0]
+    d, e, Vh, tau = householder_tridiag(S)
+    r_ = np.zeros(k); r_[:-1] += np.abs(e); r_[1:] += np.abs(e)
+    tn = max(abs(float((d - r_).min())), abs(float((d + r_).max())))
+    itn = 1.0 / tn if 0.0 < tn < 1e300 else 1.0
+    ds, es = d * itn, np.append(e * itn, 0.0)
+    Y = np.zeros((k, k))
+    for j in range(k):
+        _, z = tri_eigpair(ds, es, j)
+        for jj in range(k - 3, -1, -1):      # y = H_0 ... H_{k-3} z
+            z = z - tau[jj] * (Vh[:, jj] @ z) * Vh[:, jj]
+        Y[:, j] = z
+    G = Y.T @ Y
+    defect = float(np.abs(G - np.eye(k)).max())
+    Y2 = Y @ (1.5 * np.eye(k) - 0.5 * G)
+    SY = S @ Y2
+    theta = (Y2 * SY).sum(axis=0) / (Y2 * Y2).sum(axis=0)
+    resid = float(np.abs(SY - Y2 * theta[None, :]).max())
+    smax = float(np.abs(S).max())
+    ok = defect <= 3e-8 and resid <= 64.0 * k * EPS * smax and smax <= 1e150
+    if stats is not None:
+        key = "eigh_tridiag" if ok else "eigh_jacobi"
+        stats[key] = stats.get(key, 0) + 1
+    if not ok:
+        return jacobi_eigh(S)
+    return theta, Y2
+
+
+def sym_eigh(S, eigh="jacobi", stats=None):
+    if eigh == "tridiag" and S.shape[0] >= EIGH_TRIDIAG_MIN_K:
+        return tridiag_eigh(S, stats)
+    return jacobi_eigh(S)
+
+
+def sygv(Ap, Bp, eigh="jacobi", stats=None):
     """Generalized RR: Bp = U S U^T, T = U S^-1/2, C = T^T Ap T, C Z = Z theta, Y = T Z
     (DSYGV itype=1 semantics: Y^T Bp Y = I, ascending theta; lapack_wrapper.f90:59,73)."""
-    s, U = jacobi_eigh(Bp)
+    s, U = sym_eigh(Bp, eigh, stats)
     if s.min() <= 0:
         raise RuntimeError("second_matrix projection not positive definite")
     T = U / np.sqrt(s)
     Apu = np.triu(Ap) + np.triu(Ap, 1).T
     C = T.T @ Apu @ T
-    theta, Z = jacobi_eigh(C)
+    theta, Z = sym_eigh(C, eigh, stats)
     return theta, T @ Z
 
 
@@ -159,7 +301,7 @@ def bcgs_pip2(C, V, stats=None):
 
 
 def solve_dense(A, lowest, method, max_iterations, tolerance, max_dim_sub=None, B=None, free_semantics=False,
-                diagA=None, diagB=None, apply_A=None, apply_B=None, ortho="svqb", stats=None):
+                diagA=None, diagB=None, apply_A=None, apply_B=None, ortho="svqb", stats=None, eigh="jacobi"):
     n = A.shape[0] if A is not None else diagA.size
     gev = (B is not None) or (apply_B is not None)
     mulA = (lambda X: A @ X) if apply_A is None else apply_A
@@ -180,9 +322,9 @@ def solve_dense(A, lowest, method, max_iterations, tolerance, max_dim_sub=None, 
     theta = Y = None
     for it in range(1, max_iterations + 1):
         if gev:
-            theta, Y = sygv(Ap, Bp)
+            theta, Y = sygv(Ap, Bp, eigh, stats)
         else:
-            theta, Y = jacobi_eigh(Ap)
+            theta, Y = sym_eigh(Ap, eigh, stats)
         R = AV @ Y - ((BV if gev else V) @ Y) * theta[None, :]
         errs = np.sqrt((R[:, :lowest] ** 2).sum(axis=0))
         trace_k.append(k); trace_err.append(errs.max())

@@ -125,3 +125,56 @@ def test_bcgs_pip2_rejects_a_dependent_block_and_falls_back():
     stats = {}
     dm.bcgs_pip2(C2, V, stats)
     assert stats == {"pip_fallbacks": 1}
+
+
+def test_tridiagonal_eigensolver_model_matches_lapack():
+    rng = np.random.default_rng(11)
+    for k in (16, 33, 64, 100):
+        M = rng.standard_normal((k, k))
+        S = (M + M.T) / 2 + np.diag(np.arange(k, dtype=float))
+        stats = {}
+        w, Y = dm.tridiag_eigh(S, stats)
+        assert stats == {"eigh_tridiag": 1}
+        assert np.abs(w - np.linalg.eigvalsh(S)).max() < 1e-12 * np.abs(w).max()
+        assert np.abs(Y.T @ Y - np.eye(k)).max() < 1e-13
+        assert np.abs(S @ Y - Y * w[None, :]).max() < 1e-12 * np.abs(S).max()
+    # the projected matrices of the solver: diagonally dominant with a sorted diagonal, tiny couplings
+    S = np.diag(np.sort(rng.uniform(1, 50, 32))) + 1e-4 * (M[:32, :32] + M[:32, :32].T)
+    w, Y = dm.tridiag_eigh(S)
+    assert np.abs(w - np.linalg.eigvalsh(S)).max() < 1e-13 * np.abs(w).max()
+
+
+def test_tridiagonal_eigensolver_model_guard_refuses_degenerate_spectra():
+    """Independent eigenvector computations cannot separate an exactly degenerate eigenvalue: the guard must see it
+    and the Jacobi solver must take over (csrc/trideig.cu, step 4)."""
+    rng = np.random.default_rng(12)
+    k = 24
+    Q, _ = np.linalg.qr(rng.standard_normal((k, k)))
+    lam = np.arange(k, dtype=float); lam[5] = lam[6] = lam[7] = 3.0
+    S = (Q * lam[None, :]) @ Q.T
+    S = (S + S.T) / 2
+    stats = {}
+    w, Y = dm.tridiag_eigh(S, stats)
+    assert stats == {"eigh_jacobi": 1}
+    assert np.abs(np.sort(w) - np.sort(lam)).max() < 1e-12 * k
+    assert np.abs(Y.T @ Y - np.eye(k)).max() < 1e-12
+
+
+@pytest.mark.parametrize("name", ["readme_std_DPR", "readme_gev_DPR", "main_f90_DPR", "collapse_n1000_DPR",
+                                  "collapse_n1000_gev_DPR"])
+def test_model_round2_flow_parity_with_oracle(name, golden_cases):
+    """The complete r02 flow -- tridiagonal Rayleigh-Ritz for k >= 16 and BCGS-PIP2 expansion -- against the oracle:
+    same iteration count and basis schedule, eigenvalues to 1e-10, eigenvectors to 1e-8 up to sign."""
+    g = golden_cases[name]
+    A, B = case_inputs(name)
+    stats = {}
+    ev, X, iters, tk, te = dm.solve_dense(A, g["lowest"], "DPR", g["max_iterations"], g["tolerance"],
+                                          g["max_dim_sub"], B, ortho="pip", stats=stats, eigh="tridiag")
+    assert iters == g["iters"] and list(tk) == g["trace_k"]
+    assert np.abs(ev - np.array(g["eigenvalues"])).max() / np.abs(ev).max() < 1e-10
+    r = orc.generalized_eigensolver(A, g["lowest"], "DPR", g["max_iterations"], g["tolerance"], g["max_dim_sub"], B)
+    for j in range(g["lowest"]):
+        s = np.sign(X[:, j] @ r.eigenvectors[:, j])
+        assert np.abs(s * X[:, j] - r.eigenvectors[:, j]).max() < 1e-8
+    if max(tk) >= dm.EIGH_TRIDIAG_MIN_K:
+        assert stats.get("eigh_tridiag", 0) >= 1, stats
