@@ -220,14 +220,16 @@ def sygv(Ap, Bp, eigh="jacobi", stats=None):
     return theta, T @ Z
 
 
-def svqb(C, V, passes=2):
-    """Orthonormalise the block C against V (orthonormal) and itself."""
+def svqb(C, V, passes=2, reduce=None, rows=None):
+    """Orthonormalise the block C against V (orthonormal) and itself.  `reduce` sums a small matrix over the ranks
+    (row-block sharded run: C and V are this rank's rows, `rows` = (first row, total rows))."""
+    red = reduce or (lambda x: x)
     n, b = C.shape
-    cn = np.sqrt((C * C).sum(axis=0))
+    cn = np.sqrt(red((C * C).sum(axis=0)))
     C = C / np.where(cn > 0, cn, 1.0)
     for _ in range(passes):
-        C = C - V @ (V.T @ C)
-        G = C.T @ C
+        C = C - V @ red(V.T @ C)
+        G = red(C.T @ C)
         d = np.diag(G).copy()
         D = np.where(d > 0, 1.0 / np.sqrt(np.where(d > 0, d, 1.0)), 0.0)
         Gs = G * D[:, None] * D[None, :]
@@ -239,7 +241,8 @@ def svqb(C, V, passes=2):
         C = C @ T
         if bad.any():
             rng = np.random.default_rng(1234)
-            C[:, bad] = rng.uniform(-1, 1, size=(n, int(bad.sum())))
+            r0, ntot = rows if rows is not None else (0, n)
+            C[:, bad] = rng.uniform(-1, 1, size=(ntot, int(bad.sum())))[r0:r0 + n]
     return C
 
 
@@ -282,22 +285,95 @@ def pip_small(H, Gc, mode):
     return np.vstack([-H @ Tm, Tm]), (m0, m1, flag, 0.0)
 
 
-def bcgs_pip2(C, V, stats=None):
+def bcgs_pip2(C, V, stats=None, reduce=None, rows=None):
     """csrc/solver.cu orthonormalize_block_pip + pip_confirm: two passes of block classical Gram-Schmidt with the
     Pythagorean inner product; any raised flag, or a second pass that did not start from a block orthonormal to 1e-6,
-    rejects the result and the block is rebuilt from the corrections by the SVQB loop."""
-    M1, f1 = pip_small(V.T @ C, C.T @ C, 0)
+    rejects the result and the block is rebuilt from the corrections by the SVQB loop.  Sharded run: ONE reduction per
+    pass, of the stacked block [V C]^T C (projection coefficients and Gram matrix together)."""
+    red = reduce or (lambda x: x)
+    kold = V.shape[1]
+    Gall = red(np.hstack([V, C]).T @ C)
+    M1, f1 = pip_small(Gall[:kold], Gall[kold:], 0)
     ok = M1 is not None
     if ok:
         C1 = np.hstack([V, C]) @ M1
-        M2, f2 = pip_small(V.T @ C1, C1.T @ C1, 1)
+        Gall = red(np.hstack([V, C1]).T @ C1)
+        M2, f2 = pip_small(Gall[:kold], Gall[kold:], 1)
         ok = M2 is not None and f1[2] == 0.0 and f1[3] == 0.0 and f2[2] == 0.0 and f2[3] == 0.0 and \
             f2[0] < 1e-6 and f2[1] < 1e-6
     if stats is not None:
         stats["pip_accepted" if ok else "pip_fallbacks"] = stats.get("pip_accepted" if ok else "pip_fallbacks", 0) + 1
     if not ok:
-        return svqb(C, V)
+        return svqb(C, V, reduce=reduce, rows=rows)
     return np.hstack([V, C1]) @ M2
+
+
+def solve_dense_sharded(A_loc, r0, n, lowest, max_iterations, tolerance, max_dim_sub, B_loc, allreduce, allgather_rows,
+                        eigh="tridiag", stats=None):
+    """The row-block sharded driver loop (solver.cu with comm.active()), DPR: this rank holds the
+    rows r0 .. r0 + nl of A (and B), of the basis V and of AV / BV.  Exchanged per iteration: the k x b projection
+    blocks, the stacked Gram block of each orthonormalisation pass and the residual norm partials (`allreduce`), and
+    the rows of the new basis block (`allgather_rows`) that the block matvec needs in full.  Rayleigh-Ritz is
+    replicated.  Everything else is local to the rows."""
+    nl = A_loc.shape[0]
+    own = np.arange(nl)
+    gev = B_loc is not None
+    dA_loc = A_loc[own, r0 + own].copy()
+    dB_loc = B_loc[own, r0 + own].copy() if gev else np.ones(nl)
+    dA = allgather_rows(dA_loc[:, None])[:, 0]
+    k = 2 * lowest
+    max_dim = max_dim_sub if max_dim_sub else 10 * lowest
+    idx = np.argsort(dA, kind="stable")[:k]
+    Vfull = np.zeros((n, k)); Vfull[idx, np.arange(k)] = 1.0
+    V = Vfull[r0:r0 + nl].copy()
+    AV = A_loc @ Vfull
+    BV = B_loc @ Vfull if gev else None
+    Ap = allreduce(V.T @ AV)
+    Bp = allreduce(V.T @ BV) if gev else None
+    has_conv = np.zeros(lowest, dtype=bool)
+    trace_k = []
+    iters = max_iterations + 1
+    theta = Y = None
+    for it in range(1, max_iterations + 1):
+        theta, Y = sygv(Ap, Bp, eigh, stats) if gev else sym_eigh(Ap, eigh, stats)
+        R = AV @ Y - ((BV if gev else V) @ Y) * theta[None, :]
+        errs = np.sqrt(allreduce((R[:, :lowest] ** 2).sum(axis=0)))
+        trace_k.append(k)
+        has_conv |= errs < tolerance
+        if has_conv.all():
+            iters = it
+            break
+        if k <= max_dim:
+            C = R / (theta[None, :] * dB_loc[:, None] - dA_loc[:, None])
+            Q = bcgs_pip2(C, V, stats, reduce=allreduce, rows=(r0, n))
+            Qfull = allgather_rows(Q)
+            Vn = np.hstack([V, Q])
+            AQ = A_loc @ Qfull
+            blk = allreduce(Vn.T @ AQ)
+            Apn = np.zeros((2 * k, 2 * k)); Apn[:k, :k] = Ap
+            Apn[:, k:] = blk; Apn[k:, :k] = blk[:k, :].T
+            AV = np.hstack([AV, AQ]); Ap = Apn
+            if gev:
+                BQ = B_loc @ Qfull
+                blk = allreduce(Vn.T @ BQ)
+                Bpn = np.zeros((2 * k, 2 * k)); Bpn[:k, :k] = Bp
+                Bpn[:, k:] = blk; Bpn[k:, :k] = blk[:k, :].T
+                BV = np.hstack([BV, BQ]); Bp = Bpn
+            V = Vn
+            k *= 2
+        else:
+            Yc = Y[:, :2 * lowest]
+            V = V @ Yc; AV = AV @ Yc
+            if gev:
+                BV = BV @ Yc
+                s, U = jacobi_eigh(allreduce(V.T @ V))
+                T = U / np.sqrt(s)
+                V = V @ T; AV = AV @ T; BV = BV @ T
+                Bp = allreduce(V.T @ BV)
+            Ap = allreduce(V.T @ AV)
+            k = 2 * lowest
+    X = allgather_rows(V @ Y[:, :lowest])
+    return theta[:lowest].copy(), X, iters, np.array(trace_k)
 
 
 def solve_dense(A, lowest, method, max_iterations, tolerance, max_dim_sub=None, B=None, free_semantics=False,
