@@ -467,6 +467,14 @@ GJD_MAXIT = 40
 GJD_DFLOOR = 1e-8
 
 
+def gjd_inner_limits(outer_tolerance):
+    """r02 (csrc/gjd.cu:218-220): the inner solve is never looser than the outer tolerance -- relative residual
+    min(1e-8, max(tolerance, 1e-14)), and 8 more inner iterations per decade below 1e-8."""
+    rtol = min(GJD_RTOL, max(outer_tolerance, 1e-14))
+    maxit = GJD_MAXIT + (int(np.ceil(8.0 * np.log10(GJD_RTOL / rtol))) if rtol < GJD_RTOL else 0)
+    return rtol, maxit
+
+
 def gjd_block_minres(mulA, mulB, theta, U, W, R, dA, dB, rtol=GJD_RTOL, maxit=GJD_MAXIT):
     n, k = R.shape
     dinv = 1.0 / np.maximum(np.abs(dA[:, None] - theta[None, :] * dB[:, None]), GJD_DFLOOR)
@@ -561,7 +569,9 @@ def solve_dense_gjd(A, lowest, max_iterations, tolerance, max_dim_sub=None, B=No
             iters = it
             break
         if k <= max_dim:
-            C, nin = gjd_block_minres(lambda X: A @ X, (lambda X: B @ X) if gev else None, theta, U, W, R, dA, dB)
+            rtol, maxit = gjd_inner_limits(tolerance)
+            C, nin = gjd_block_minres(lambda X: A @ X, (lambda X: B @ X) if gev else None, theta, U, W, R, dA, dB,
+                                      rtol, maxit)
             inner.append(nin)
             Q = svqb(C, V) if ortho == "svqb" else bcgs_pip2(C, V, stats)
             AQ = A @ Q
