@@ -80,3 +80,48 @@ def test_tall_skinny_gemm_uses_the_tensor_pipe():
                 runs.append(cur)
                 cur = 0
         assert max(runs) >= 12, max(runs)
+
+
+def _resource_usage():
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    if not os.path.exists(LIB):
+        pytest.skip("library not built")
+    out = subprocess.run([tool, "--dump-resource-usage", LIB], capture_output=True, text=True, timeout=300).stdout
+    usage, cur = {}, None
+    for ln in out.splitlines():
+        m = re.search(r"Function (\S+):", ln)
+        if m:
+            cur = m.group(1)
+            continue
+        m = re.search(r"REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", ln)
+        if m and cur:
+            usage[cur] = dict(zip(("reg", "stack", "shared", "local"), map(int, m.groups())))
+            cur = None
+    return usage
+
+
+def test_hot_kernels_do_not_spill():
+    """Register budgets of the kernels the solve time is made of (ptxas resource usage of the shipped cubin): the block
+    matvec and the fused residual keep everything in registers; the tall-skinny GEMM variants do except the 4-warp-group
+    ones, which trade a few spilled words for 512 threads at 128 registers; the single-CTA small-matrix kernels stay
+    within a few words."""
+    usage = _resource_usage()
+    pick = lambda frag: {k: v for k, v in usage.items() if frag in k}
+    mv = pick("matvec_kernel")
+    assert len(mv) == 16
+    assert all(v["stack"] == 0 and v["local"] == 0 and v["reg"] <= 168 for v in mv.values()), mv
+    rs = pick("resid_dmma_kernel")
+    assert len(rs) == 2 and all(v["stack"] == 0 for v in rs.values()), rs
+    gm = pick("gemm_dmma_kernel")
+    assert len(gm) == 18
+    spilled = {k: v for k, v in gm.items() if v["stack"] > 0}
+    assert len(spilled) == 6 and all(v["reg"] == 128 and v["stack"] <= 96 for v in spilled.values()), spilled
+    tri = pick("tridiag_reg_kernel")
+    assert tri and all(v["stack"] <= 32 for v in tri.values()), tri
+    ev = pick("tri_eigvec_kernel")
+    assert ev and all(v["stack"] == 0 for v in ev.values()), ev
+    fr = pick("free_dmma_kernel")
+    assert fr and all(v["reg"] <= 128 and v["stack"] <= 40 for v in fr.values()), fr   # 2 CTAs of 256 threads per SM
+    assert all(v["local"] == 0 for v in usage.values())
