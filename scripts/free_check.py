@@ -1,5 +1,7 @@
-import sys, time
-sys.path.insert(0, "/root/repo")
+"""Matrix-free benchmark operator at n = 200,000 on one GPU: iterations, solve time, basis schedule and how often the
+fast block orthonormalisation was rejected (the configs[4] regression check of r02: nearly parallel DPR corrections)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import fortran_davidson_b200 as fd
 s = fd.DavidsonSolver()
 n = 200000
