@@ -193,3 +193,26 @@ def test_model_gjd_inner_solve_follows_a_tight_outer_tolerance():
     assert abs(iters - r.iters) <= 1 and max(inner) <= 72
     assert np.abs(ev - r.eigenvalues).max() / np.abs(ev).max() < 1e-12
     assert np.sqrt(((A @ X - X * ev[None, :]) ** 2).sum(axis=0)).max() < 1e-12
+
+
+def test_model_round2_flow_seeded_sweep_against_oracle():
+    """12 seeded problems beyond the named cases (size, `lowest`, sparsity, subspace limit with collapses, with and
+    without second_matrix): the r02 device flow takes exactly the oracle's iteration count and basis schedule and
+    lands on its eigenvalues to 1e-12."""
+    rng = np.random.default_rng(777)
+    for t in range(12):
+        n = int(rng.integers(200, 900))
+        lowest = int(rng.integers(1, 7))
+        sp = float(10.0 ** rng.uniform(-3, -1.5))
+        gev = bool(t % 2)
+        max_dim = int(lowest * rng.integers(2, 9)) if t % 4 == 0 else None
+        A = orc.generate_diagonal_dominant(n, sp, seed=1000 + t)
+        B = orc.generate_diagonal_dominant(n, sp, 1.0, seed=2000 + t) if gev else None
+        r = orc.generalized_eigensolver(A, lowest, "DPR", 80, 1e-8, max_dim, B)
+        stats = {}
+        ev, X, iters, tk, te = dm.solve_dense(A, lowest, "DPR", 80, 1e-8, max_dim, B, ortho="pip", stats=stats,
+                                              eigh="tridiag")
+        label = (t, n, lowest, gev, max_dim)
+        assert iters == r.iters and list(tk) == [int(k) for k in r.trace_k], label
+        assert np.abs(ev - r.eigenvalues).max() <= 1e-12 * np.abs(ev).max(), label
+        assert stats.get("pip_fallbacks", 0) == 0, (label, stats)
