@@ -50,3 +50,44 @@ def test_golden_files_of_the_parity_checks():
     w = bench.W()
     assert bench.is_headline(w) and not bench.is_headline(bench.W(n=20000)) and not bench.is_headline(bench.W(gev=True))
     assert "configs[2]" in bench.workload_config(w, 8)["workload"] and "8 GPU" in bench.workload_config(w, 8)["workload"]
+
+
+def test_bench_parity_checker_accepts_the_golden_and_rejects_deviations():
+    """bench.py's `parity_check` is what turns a wrong result at any N into a non-zero exit: feed it a synthetic
+    result built from the golden file (pass, also with flipped eigenvector signs), then break one thing at a time."""
+    import types
+    sys.path.insert(0, ROOT)
+    import bench
+    g = bench.golden_full_size()
+    n, L = g["n"], g["lowest"]
+    probes = np.asarray(g["probe_rows"])
+    vec = np.zeros((n, L))
+    for j, fp in enumerate(g["eigenvectors"]):
+        vec[probes, j] = fp["probes"]
+        vec[fp["imax"], j] = fp["vmax"]
+        spare = next(i for i in range(n) if i != fp["imax"] and i not in set(probes.tolist()))
+        rest = fp["norm"] ** 2 - float((vec[:, j] ** 2).sum())
+        assert rest >= 0
+        vec[spare, j] = np.sqrt(rest)
+        if j % 2:
+            vec[:, j] *= -1.0                      # eigenvectors are defined up to sign
+    trace = g["trace_k"]
+    st = types.SimpleNamespace(trace_k=trace + [0] * 8, trace_len=len(trace))
+    cx = types.SimpleNamespace(np=np, world=4)
+    w = bench.W()
+
+    def check(ev=None, iters=None, vec_=None, max_res=1e-9, trace_=None):
+        s = st if trace_ is None else types.SimpleNamespace(trace_k=trace_ + [0] * 8, trace_len=len(trace_))
+        res = {"ev": np.asarray(g["eigenvalues"]) if ev is None else ev, "iters": g["iters"] if iters is None else iters,
+               "st": s}
+        return bench.golden_parity(cx, w, res, max_res, vec if vec_ is None else vec_)
+
+    ok = check()
+    assert ok["pass"] and ok["n_gpus"] == 4 and ok["eigenvector_probe_max_abs_err"] < 1e-12
+    ev = np.asarray(g["eigenvalues"]).copy(); ev[7] *= 1 + 1e-9
+    assert not check(ev=ev)["pass"]                                   # eigenvalue off by 1e-9 relative
+    assert not check(iters=g["iters"] + 1)["pass"]                    # full-size run: iteration count must be equal
+    assert not check(trace_=[32, 64, 32])["pass"]                     # another basis schedule
+    assert not check(max_res=2e-8)["pass"]                            # residual above the tolerance
+    bad = vec.copy(); bad[probes[3], 5] += 1e-7
+    assert not check(vec_=bad)["pass"]                                # one eigenvector entry off by 1e-7
