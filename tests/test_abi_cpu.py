@@ -442,3 +442,31 @@ def test_fortran_shim_blocks_balance_and_c_calls_pass_the_declared_argument_coun
             assert len(actual) == nargs[name], (no, name, len(actual), nargs[name])
             calls += 1
     assert calls >= 13, calls
+
+
+def test_python_call_sites_pass_the_declared_argument_count():
+    """ctypes binds by name and checks nothing: a call with one argument too few reads garbage from a register.  Every
+    `<lib>.dav_*(...)` call in the package, bench.py, the tests, the examples and the scripts is counted against the
+    prototype in include/davidson_b200.h."""
+    import ast
+    protos, _ = _c_prototypes(open(os.path.join(ROOT, "include", "davidson_b200.h")).read())
+    files = [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]
+    for sub in ("fortran_davidson_b200", "tests", "examples", "scripts"):
+        d = os.path.join(ROOT, sub)
+        files += [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith(".py")]
+    calls, seen = 0, set()
+    for path in files:
+        tree = ast.parse(open(path).read(), path)
+        for node in ast.walk(tree):
+            if not (isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute)):
+                continue
+            name = node.func.attr
+            if not name.startswith("dav_") or name not in protos:
+                continue
+            if any(isinstance(a, ast.Starred) for a in node.args) or node.keywords:
+                continue
+            want = len(protos[name][1])
+            assert len(node.args) == want, (os.path.relpath(path, ROOT), node.lineno, name, len(node.args), want)
+            calls += 1
+            seen.add(name)
+    assert calls >= 60 and len(seen) >= 40, (calls, len(seen))
