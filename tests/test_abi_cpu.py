@@ -454,9 +454,10 @@ def test_python_call_sites_pass_the_declared_argument_count():
     for sub in ("fortran_davidson_b200", "tests", "examples", "scripts"):
         d = os.path.join(ROOT, sub)
         files += [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith(".py")]
-    calls, seen = 0, set()
+    calls, seen, sources = 0, set(), {}
     for path in files:
-        tree = ast.parse(open(path).read(), path)
+        sources[path] = open(path).read()
+        tree = ast.parse(sources[path], path)
         for node in ast.walk(tree):
             if not (isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute)):
                 continue
@@ -466,7 +467,15 @@ def test_python_call_sites_pass_the_declared_argument_count():
             if any(isinstance(a, ast.Starred) for a in node.args) or node.keywords:
                 continue
             want = len(protos[name][1])
-            assert len(node.args) == want, (os.path.relpath(path, ROOT), node.lineno, name, len(node.args), want)
+            where = (os.path.relpath(path, ROOT), node.lineno, name)
+            assert len(node.args) == want, where + (len(node.args), want)
+            # 64-bit integers and doubles must be passed as ctypes objects (a bare Python int travels as a C int, a
+            # bare float is refused) unless the file declares argtypes for that function
+            if (name + ".argtypes") not in sources[path]:
+                for a, ct in zip(node.args, protos[name][1]):
+                    if ct in ("int64_t", "uint64_t", "double"):
+                        fn = ast.unparse(a.func).split(".")[-1] if isinstance(a, ast.Call) else ""
+                        assert fn in ("c_int64", "c_uint64", "c_double", "c_longlong"), where + (ct, ast.unparse(a))
             calls += 1
             seen.add(name)
     assert calls >= 60 and len(seen) >= 40, (calls, len(seen))
